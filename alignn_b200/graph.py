@@ -1,0 +1,298 @@
+"""Graph container for the edge-gated conv hot path.
+
+The reference hands `dgl.DGLGraph` objects (`g`, `lg`) to `ALIGNN.forward`
+(alignn/models/alignn.py:282-294); DGL is a third-party wheel that is not part of
+this build.  `Graph` exposes the subset of the DGLGraph API the reference's model
+and collate code touches and, in addition, carries the
+**sorted-CSR edge index** the CUDA kernels consume:
+
+    in_ptr [Nn+1], in_eid [Ne]   edge ids stably sorted by destination  (in-CSR)
+    out_ptr[Nn+1], out_eid[Ne]   edge ids stably sorted by source       (out-CSR)
+
+all int32.  The index is integer-exact, built once on the host when the graph is
+made (the reference likewise builds graph structure on the CPU and caches it,
+alignn/graphs.py:544,588; lmdb_dataset.py:220-224) and moves with `.to(device)`.
+`line_graph()` emits L(g) with its edges already destination-sorted so that
+`in_eid` is the identity for the graph that carries ~92 % of the bytes.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+__all__ = ["Graph", "EdgeIndex", "batch", "unbatch", "reverse", "graph", "as_graph", "bond_cosines"]
+
+
+def _np(a):
+    if isinstance(a, torch.Tensor):
+        return a.detach().cpu().numpy()
+    return np.asarray(a)
+
+
+class EdgeIndex:
+    """Sorted-CSR edge index of one graph (both orientations), int32 tensors."""
+
+    __slots__ = ("src", "dst", "in_ptr", "in_eid", "out_ptr", "out_eid", "dst_sorted",
+                 "max_in_deg", "num_nodes")
+
+    def __init__(self, src, dst, in_ptr, in_eid, out_ptr, out_eid, dst_sorted, max_in_deg, num_nodes):
+        self.src, self.dst = src, dst
+        self.in_ptr, self.in_eid = in_ptr, in_eid
+        self.out_ptr, self.out_eid = out_ptr, out_eid
+        self.dst_sorted = bool(dst_sorted)
+        self.max_in_deg = int(max_in_deg)
+        self.num_nodes = int(num_nodes)
+
+    @staticmethod
+    def build(src: np.ndarray, dst: np.ndarray, num_nodes: int) -> "EdgeIndex":
+        """Stable counting sort by dst and by src.  Bit-exact vs oracle.csr_by_key."""
+        src = np.ascontiguousarray(src, dtype=np.int64)
+        dst = np.ascontiguousarray(dst, dtype=np.int64)
+        E = src.shape[0]
+        if E >= 2 ** 31 or num_nodes >= 2 ** 31:
+            raise ValueError("graph too large for int32 edge index")
+        if E and (src.min() < 0 or dst.min() < 0 or src.max() >= num_nodes or dst.max() >= num_nodes):
+            raise ValueError("edge endpoint out of range")
+        indeg = np.bincount(dst, minlength=num_nodes)
+        outdeg = np.bincount(src, minlength=num_nodes)
+        in_ptr = np.zeros(num_nodes + 1, dtype=np.int64)
+        out_ptr = np.zeros(num_nodes + 1, dtype=np.int64)
+        np.cumsum(indeg, out=in_ptr[1:])
+        np.cumsum(outdeg, out=out_ptr[1:])
+        dst_sorted = bool(E == 0 or np.all(dst[1:] >= dst[:-1]))
+        in_eid = np.arange(E, dtype=np.int64) if dst_sorted else np.argsort(dst, kind="stable")
+        out_eid = np.argsort(src, kind="stable")
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32))  # noqa: E731
+        return EdgeIndex(t(src), t(dst), t(in_ptr), t(in_eid), t(out_ptr), t(out_eid),
+                         dst_sorted, int(indeg.max()) if E else 0, num_nodes)
+
+    _FIELDS = ("src", "dst", "in_ptr", "in_eid", "out_ptr", "out_eid")
+
+    def to(self, device, non_blocking=False) -> "EdgeIndex":
+        moved = [getattr(self, f).to(device, non_blocking=non_blocking) for f in self._FIELDS]
+        return EdgeIndex(*moved, self.dst_sorted, self.max_in_deg, self.num_nodes)
+
+    def pin_memory(self) -> "EdgeIndex":
+        moved = [getattr(self, f).pin_memory() for f in self._FIELDS]
+        return EdgeIndex(*moved, self.dst_sorted, self.max_in_deg, self.num_nodes)
+
+    def nbytes(self) -> int:
+        return sum(getattr(self, f).numel() * 4 for f in self._FIELDS)
+
+
+class _EdgeBatch:
+    """What a user function passed to `apply_edges` sees (edges.src / .dst / .data)."""
+
+    def __init__(self, g: "Graph"):
+        s, d = g.index.src.long(), g.index.dst.long()
+        self.src = {k: v[s] for k, v in g.ndata.items()}
+        self.dst = {k: v[d] for k, v in g.ndata.items()}
+        self.data = dict(g.edata)
+
+
+class Graph:
+    """Batched directed multigraph with feature dicts and a sorted-CSR edge index."""
+
+    def __init__(self, src=None, dst=None, num_nodes: Optional[int] = None,
+                 batch_num_nodes=None, batch_num_edges=None, *, _index: Optional[EdgeIndex] = None):
+        if _index is None:
+            src, dst = _np(src).reshape(-1), _np(dst).reshape(-1)
+            if num_nodes is None:
+                num_nodes = int(max(src.max(), dst.max())) + 1 if src.size else 0
+            _index = EdgeIndex.build(src, dst, int(num_nodes))
+        self.index = _index
+        self._n = _index.num_nodes
+        E = int(_index.src.numel())
+        self._bnn = torch.tensor([self._n], dtype=torch.int64) if batch_num_nodes is None \
+            else torch.as_tensor(batch_num_nodes, dtype=torch.int64).reshape(-1).cpu()
+        self._bne = torch.tensor([E], dtype=torch.int64) if batch_num_edges is None \
+            else torch.as_tensor(batch_num_edges, dtype=torch.int64).reshape(-1).cpu()
+        if int(self._bnn.sum()) != self._n or int(self._bne.sum()) != E:
+            raise ValueError("batch_num_nodes / batch_num_edges do not add up")
+        self.ndata: dict = {}
+        self.edata: dict = {}
+        self._seg = None  # cached per-graph node offsets on device (for pooling)
+
+    # ---- DGLGraph API subset -----------------------------
+    def edges(self):
+        return self.index.src, self.index.dst
+
+    def num_nodes(self) -> int:
+        return self._n
+
+    def num_edges(self) -> int:
+        return int(self.index.src.numel())
+
+    number_of_nodes = num_nodes
+    number_of_edges = num_edges
+
+    @property
+    def batch_size(self) -> int:
+        return int(self._bnn.numel())
+
+    def batch_num_nodes(self):
+        return self._bnn
+
+    def batch_num_edges(self):
+        return self._bne
+
+    @property
+    def device(self):
+        return self.index.src.device
+
+    def local_var(self) -> "Graph":
+        """Shallow copy: same structure, fresh feature dicts (reference: alignn.py:88,159,295)."""
+        g = Graph(batch_num_nodes=self._bnn, batch_num_edges=self._bne, _index=self.index)
+        g.ndata.update(self.ndata)
+        g.edata.update(self.edata)
+        g._seg = self._seg
+        return g
+
+    def to(self, device, non_blocking: bool = False) -> "Graph":
+        device = torch.device(device)
+        if device == self.device:
+            return self
+        g = Graph(batch_num_nodes=self._bnn, batch_num_edges=self._bne,
+                  _index=self.index.to(device, non_blocking))
+        g.ndata = {k: v.to(device, non_blocking=non_blocking) for k, v in self.ndata.items()}
+        g.edata = {k: v.to(device, non_blocking=non_blocking) for k, v in self.edata.items()}
+        return g
+
+    def pin_memory(self) -> "Graph":
+        g = Graph(batch_num_nodes=self._bnn, batch_num_edges=self._bne, _index=self.index.pin_memory())
+        g.ndata = {k: v.pin_memory() for k, v in self.ndata.items()}
+        g.edata = {k: v.pin_memory() for k, v in self.edata.items()}
+        return g
+
+    def nbytes(self) -> int:
+        """Bytes moved by `.to(device)` (structure + features)."""
+        n = self.index.nbytes()
+        for d in (self.ndata, self.edata):
+            n += sum(v.numel() * v.element_size() for v in d.values())
+        return n
+
+    def apply_edges(self, func):
+        """User-defined edge function (e.g. compute_bond_cosines, alignn/graphs.py:847)."""
+        self.edata.update(func(_EdgeBatch(self)))
+
+    def node_graph_offsets(self) -> torch.Tensor:
+        """int32 [B+1] prefix of batch_num_nodes on this graph's device (per-graph pooling)."""
+        if self._seg is None or self._seg.device != self.device:
+            off = torch.zeros(self.batch_size + 1, dtype=torch.int32)
+            off[1:] = torch.cumsum(self._bnn, 0).to(torch.int32)
+            self._seg = off.to(self.device)
+        return self._seg
+
+    def line_graph(self, backtracking: bool = True, shared: bool = False) -> "Graph":
+        """L(g): node i == edge i of g; edge (i -> j) iff dst(i) == src(j) and i != j.
+
+        Same edge SET as `g.line_graph(shared=True)` at alignn/graphs.py:588 (backtracking
+        pairs kept); emitted sorted by (j, i) -- destination-major -- instead of DGL's
+        source-major order.  L(g)'s edge order is never observable (z is consumed, not
+        returned), and within one destination the sources stay ascending, so segment sums
+        add in the same order as the reference.
+        """
+        if not backtracking:
+            raise NotImplementedError("backtracking=False is not used by the reference")
+        ix = self.index
+        src = ix.src.cpu().numpy().astype(np.int64)
+        in_ptr = ix.in_ptr.cpu().numpy().astype(np.int64)
+        in_eid = ix.in_eid.cpu().numpy().astype(np.int64)
+        E = src.shape[0]
+        deg = in_ptr[src + 1] - in_ptr[src]                 # candidates i for each j
+        lj = np.repeat(np.arange(E, dtype=np.int64), deg)
+        start = np.repeat(in_ptr[src], deg)
+        off = np.arange(lj.shape[0], dtype=np.int64) - np.repeat(np.cumsum(deg) - deg, deg)
+        li = in_eid[start + off]
+        keep = li != lj                                      # only self-loop bonds pair with themselves
+        li, lj = li[keep], lj[keep]
+        eoff = np.cumsum(self._bne.numpy())
+        lbne = np.bincount(np.searchsorted(eoff, lj, side="right"), minlength=len(eoff))
+        lg = Graph(li, lj, E, self._bne.clone(), lbne)
+        if self.device.type != "cpu":
+            lg = lg.to(self.device)
+        if shared:
+            lg.ndata.update(self.edata)
+        return lg
+
+
+# ---- module-level helpers mirroring dgl.* ------------------------------------
+def graph(data, num_nodes=None) -> Graph:
+    """dgl.graph((src, dst), num_nodes=...) (alignn/graphs.py:544)."""
+    return Graph(data[0], data[1], num_nodes)
+
+
+def batch(graphs: Sequence[Graph]) -> Graph:
+    """dgl.batch (alignn/lmdb_dataset.py:93-94): concatenate, offset ids, keep order."""
+    noff, s, d = 0, [], []
+    for g in graphs:
+        s.append(g.index.src.cpu().numpy().astype(np.int64) + noff)
+        d.append(g.index.dst.cpu().numpy().astype(np.int64) + noff)
+        noff += g.num_nodes()
+    bg = Graph(np.concatenate(s), np.concatenate(d), noff,
+               torch.cat([g.batch_num_nodes() for g in graphs]),
+               torch.cat([g.batch_num_edges() for g in graphs]))
+    for k in graphs[0].ndata:
+        bg.ndata[k] = torch.cat([g.ndata[k] for g in graphs], 0)
+    for k in graphs[0].edata:
+        bg.edata[k] = torch.cat([g.edata[k] for g in graphs], 0)
+    return bg
+
+
+def unbatch(g: Graph):
+    """dgl.unbatch (alignn_atomwise.py:492)."""
+    out, no, eo = [], 0, 0
+    src, dst = g.index.src.cpu().numpy(), g.index.dst.cpu().numpy()
+    for n, e in zip(g.batch_num_nodes().tolist(), g.batch_num_edges().tolist()):
+        h = Graph(src[eo:eo + e] - no, dst[eo:eo + e] - no, n)
+        h.ndata = {k: v[no:no + n] for k, v in g.ndata.items()}
+        h.edata = {k: v[eo:eo + e] for k, v in g.edata.items()}
+        out.append(h)
+        no, eo = no + n, eo + e
+    return out
+
+
+def reverse(g: Graph, copy_ndata: bool = True, copy_edata: bool = False) -> Graph:
+    """dgl.reverse (alignn_atomwise.py:555): swap src/dst, keep edge ids."""
+    ix = g.index
+    r = Graph(batch_num_nodes=g.batch_num_nodes(), batch_num_edges=g.batch_num_edges(),
+              _index=EdgeIndex(ix.dst, ix.src, ix.out_ptr, ix.out_eid, ix.in_ptr, ix.in_eid,
+                               False, 0, ix.num_nodes))
+    if copy_ndata:
+        r.ndata.update(g.ndata)
+    if copy_edata:
+        r.edata.update(g.edata)
+    return r
+
+
+def as_graph(g) -> Graph:
+    """Accept our Graph, or anything DGLGraph-like (edges/num_nodes/batch_num_* /ndata/edata)."""
+    if isinstance(g, Graph):
+        return g
+    cached = getattr(g, "_alignn_b200_graph", None)
+    if cached is not None:
+        return cached
+    if not (hasattr(g, "edges") and hasattr(g, "num_nodes")):
+        raise TypeError(f"expected alignn_b200.Graph or a DGLGraph-like object, got {type(g)!r}")
+    s, d = g.edges()
+    out = Graph(s, d, g.num_nodes(), g.batch_num_nodes(), g.batch_num_edges())
+    dev = s.device if isinstance(s, torch.Tensor) else torch.device("cpu")
+    if dev.type != "cpu":
+        out = out.to(dev)
+    out.ndata.update(dict(g.ndata))
+    out.edata.update(dict(g.edata))
+    try:
+        g._alignn_b200_graph = out
+    except Exception:
+        pass
+    return out
+
+
+def bond_cosines(r: torch.Tensor, lg: Graph) -> torch.Tensor:
+    """Bond-angle cosines for every L(g) edge (compute_bond_cosines, alignn/graphs.py:847-864)."""
+    r1 = -r[lg.index.src.long()]
+    r2 = r[lg.index.dst.long()]
+    c = torch.sum(r1 * r2, dim=1) / (torch.norm(r1, dim=1) * torch.norm(r2, dim=1))
+    return torch.clamp(c, -1, 1)
