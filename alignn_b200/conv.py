@@ -1,0 +1,238 @@
+"""EdgeGatedGraphConv / ALIGNNConv on the B200 kernels.
+
+Mirrors the reference operator interface for this path:
+    EdgeGatedGraphConv(input_features, output_features, residual=True).forward(g, node_feats, edge_feats) -> (x, y)
+    ALIGNNConv(in_features, out_features).forward(g, lg, x, y, z) -> (x, y, z)
+(alignn/models/alignn.py:48-167; LayerNorm twins alignn/models/alignn_atomwise.py:127-246),
+with identical attribute / state_dict names so reference checkpoints load
+with `load_state_dict`.
+
+The four node Linear layers run as ONE [Nn,d]x[d,4d] GEMM and the edge gate as one [Ne,d]x[d,d]
+GEMM; everything else of the layer -- u_add_v, sigmoid, both update_all reductions, the division,
+both norms, SiLU, residuals -- is a single fused CUDA kernel forward and two backward
+(alignn_b200/csrc/egc_kernels.cu), called through the C ABI.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+from torch.autograd.function import once_differentiable
+
+from . import ops
+from .graph import as_graph
+from .ops import NORM_AFFINE, NORM_LAYER, NORM_STATS
+
+GATE_EPS = 1e-6   # alignn.py:109
+
+
+class _Cfg:
+    """Per-call, non-tensor configuration of the fused stage."""
+    __slots__ = ("index", "norm_nodes", "norm_edges", "residual", "need_edge_out", "ln_eps",
+                 "bn_nodes", "bn_edges", "n_aux", "e_aux")
+
+
+def _bn_eval_vectors(bn: nn.BatchNorm1d):
+    """scale/shift/mean/rstd of an eval-mode BatchNorm1d, cached on the module by tensor versions."""
+    key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+           bn.weight.device)
+    cache = getattr(bn, "_alignn_b200_eval", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    with torch.no_grad():
+        rstd = torch.rsqrt(bn.running_var + bn.eps)
+        scale = bn.weight * rstd
+        shift = bn.bias - bn.running_mean * scale
+        vecs = (scale.contiguous(), shift.contiguous(), bn.running_mean.detach().clone(), rstd.contiguous())
+    bn._alignn_b200_eval = (key, vecs)
+    return vecs
+
+
+class _EdgeGatedConvFn(torch.autograd.Function):
+    """x, y, 5 Linear (weight, bias) pairs, 2 norm (weight, bias) pairs -> (x_out, y_out)."""
+
+    @staticmethod
+    def forward(ctx, cfg: _Cfg, x, y, W_sg, b_sg, W_dg, b_dg, W_eg, b_eg, W_su, b_su, W_du, b_du, nw, nb, ew, eb):
+        ix = cfg.index
+        x = x.contiguous()
+        y = y.contiguous()
+        ops.require_cuda(x, y)
+        Nn, d = x.shape
+        Ne = y.shape[0]
+        needs_grad = any(ctx.needs_input_grad)
+        # node projections P = [e_src | Bh | e_dst | src_update] (include/alignn_b200.h) and edge gate G
+        Wcat = torch.cat([W_sg, W_du, W_dg, W_su], 0)
+        bcat = torch.cat([b_sg, b_du, b_dg, b_su], 0)
+        P = torch.addmm(bcat, x, Wcat.t())
+        G = torch.addmm(b_eg, y, W_eg.t())
+
+        n_aux = e_aux = None
+        if cfg.norm_nodes == NORM_AFFINE:
+            n_aux = _bn_eval_vectors(cfg.bn_nodes)
+            e_aux = _bn_eval_vectors(cfg.bn_edges)
+            n_w, n_b, e_w, e_b = n_aux[0], n_aux[1], e_aux[0], e_aux[1]
+        elif cfg.norm_nodes == NORM_STATS:
+            n_w = n_b = e_w = e_b = None
+        else:
+            n_w, n_b, e_w, e_b = nw.contiguous(), nb.contiguous(), ew.contiguous(), eb.contiguous()
+
+        out = ops.egc_forward(ix, x, y, G, P, n_w, n_b, e_w, e_b, norm_nodes=cfg.norm_nodes,
+                              norm_edges=cfg.norm_edges, residual=cfg.residual, save=needs_grad,
+                              need_edge_out=cfg.need_edge_out, gate_eps=GATE_EPS, ln_eps=cfg.ln_eps)
+        x_out, y_out = out["x_out"], out["y_out"]
+        if cfg.norm_nodes == NORM_STATS:
+            # BatchNorm1d train mode (alignn.py:122-123): batch statistics, running-stat update
+            bnn, bne = cfg.bn_nodes, cfg.bn_edges
+            track_n = bnn.track_running_stats and bnn.running_mean is not None
+            track_e = bne.track_running_stats and bne.running_mean is not None
+            n_aux = ops.bn_finalize(out["partials"], 1, Nn, nw, nb, bnn.eps, _momentum(bnn),
+                                    bnn.running_mean if track_n else None, bnn.running_var if track_n else None)
+            x_out = ops.affine_silu_residual(out["XP"], x if cfg.residual else None, n_aux[0], n_aux[1])
+            if Ne > 0:
+                # statistics (and running buffers) are updated even when the edge output is dead
+                # (SURVEY.md App. D-11): the reference always evaluates bn_edges(m).
+                e_aux = ops.bn_finalize(out["partials"], 0, Ne, ew, eb, bne.eps, _momentum(bne),
+                                        bne.running_mean if track_e else None, bne.running_var if track_e else None)
+                if cfg.need_edge_out:
+                    y_out = ops.affine_silu_residual(out["M"], y if cfg.residual else None, e_aux[0], e_aux[1])
+            for bn in (bnn, bne):
+                if bn.track_running_stats and bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked.add_(1)
+        if needs_grad:
+            ctx.cfg = cfg
+            cfg.n_aux, cfg.e_aux = n_aux, e_aux
+            ctx.save_for_backward(x, y, P, out["M"], out["XP"], out["S"], out["H"], Wcat, W_eg, nw, nb, ew, eb)
+        ctx.y_dead = y_out is None
+        if y_out is None:       # dead edge output (or an edgeless graph): hand autograd an empty placeholder
+            y_out = x.new_empty((0, d))
+            ctx.mark_non_differentiable(y_out)
+        return x_out, y_out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gx_out, gy_out):
+        cfg = ctx.cfg
+        x, y, P, M, XP, S, H, Wcat, W_eg, nw, nb, ew, eb = ctx.saved_tensors
+        d = x.shape[1]
+        gx_out = gx_out.contiguous()
+        gy_out = None if (ctx.y_dead or gy_out is None) else gy_out.contiguous()
+        if cfg.norm_nodes == NORM_LAYER:
+            n = dict(w=nw.contiguous(), b=nb.contiguous())
+            e = dict(w=ew.contiguous(), b=eb.contiguous())
+        else:
+            sc, sh, mu, rs = cfg.n_aux
+            n = dict(w=sc, b=sh, mean=mu, rstd=rs)
+            e = {}
+            if cfg.e_aux is not None:
+                sc, sh, mu, rs = cfg.e_aux
+                e = dict(w=sc, b=sh, mean=mu, rstd=rs)
+            if cfg.norm_nodes == NORM_STATS:
+                n["c1"], n["c2"] = ops.bn_backward_reduce(XP, gx_out, n["w"], n["b"], n["mean"], n["rstd"])
+                if gy_out is not None:
+                    e["c1"], e["c2"] = ops.bn_backward_reduce(M, gy_out, e["w"], e["b"], e["mean"], e["rstd"])
+        GM, GP, vd, vs = ops.egc_backward(cfg.index, P, M, XP, S, H, gx_out, gy_out, n, e,
+                                          norm_nodes=cfg.norm_nodes, norm_edges=cfg.norm_edges,
+                                          gate_eps=GATE_EPS, ln_eps=cfg.ln_eps)
+        # GEMM halves of the backward (plain library GEMMs, fp32)
+        need = ctx.needs_input_grad
+        gx = gy = None
+        if need[1]:
+            gx = torch.addmm(gx_out, GP, Wcat) if cfg.residual else GP @ Wcat
+        if need[2]:
+            if gy_out is not None and cfg.residual:
+                gy = torch.addmm(gy_out, GM, W_eg)
+            else:
+                gy = GM @ W_eg
+        gWcat = GP.t() @ x                      # [4d, d] rows: src_gate | dst_update | dst_gate | src_update
+        gW_eg = GM.t() @ y
+        gW_sg, gW_du, gW_dg, gW_su = gWcat[0:d], gWcat[d:2 * d], gWcat[2 * d:3 * d], gWcat[3 * d:4 * d]
+        gb_sg, gb_du = vs[0], vs[1]
+        gb_su, gb_dg = vd[4], vd[5]
+        gb_eg = gb_dg                           # sum_e gm_e == sum_v sum_{e->v} gm_e
+        g_nw, g_nb = vd[2], vd[3]
+        g_ew, g_eb = (vd[0], vd[1]) if gy_out is not None else (None, None)
+        return (None, gx, gy, gW_sg, gb_sg, gW_dg, gb_dg, gW_eg, gb_eg, gW_su, gb_su, gW_du, gb_du,
+                g_nw, g_nb, g_ew, g_eb)
+
+
+def _momentum(bn: nn.BatchNorm1d) -> float:
+    if bn.momentum is None:
+        raise NotImplementedError("BatchNorm1d(momentum=None) (cumulative average) is not supported")
+    return float(bn.momentum)
+
+
+class EdgeGatedGraphConvBase(nn.Module):
+    """Edge-gated graph convolution (arXiv:1711.07553) -- shared implementation.
+
+    Parameter names follow alignn/models/alignn.py:68-76.  `norm` selects BatchNorm1d
+    (alignn.py) or LayerNorm (alignn_atomwise.py) for bn_nodes / bn_edges.
+    """
+
+    def __init__(self, input_features: int, output_features: int, residual: bool = True, norm: str = "batchnorm"):
+        super().__init__()
+        if input_features != output_features:
+            raise NotImplementedError(
+                "alignn_b200 kernels need input_features == output_features (the reference only ever "
+                "instantiates square layers; its residual path requires it, alignn.py:125-127)")
+        self.residual = residual
+        self.norm_kind = norm
+        mk = (lambda: nn.BatchNorm1d(output_features)) if norm == "batchnorm" else (lambda: nn.LayerNorm(output_features))
+        self.src_gate = nn.Linear(input_features, output_features)
+        self.dst_gate = nn.Linear(input_features, output_features)
+        self.edge_gate = nn.Linear(input_features, output_features)
+        self.bn_edges = mk()
+        self.src_update = nn.Linear(input_features, output_features)
+        self.dst_update = nn.Linear(input_features, output_features)
+        self.bn_nodes = mk()
+
+    def forward(self, g, node_feats: torch.Tensor, edge_feats: torch.Tensor, _need_edge_out: bool = True):
+        g = as_graph(g)
+        if node_feats.dtype != torch.float32 or edge_feats.dtype != torch.float32:
+            raise RuntimeError("alignn_b200.EdgeGatedGraphConv is fp32-only (the reference default dtype, "
+                               f"alignn/config.py:163); got {node_feats.dtype}")
+        if not node_feats.is_cuda:
+            raise RuntimeError("alignn_b200.EdgeGatedGraphConv has no CPU path: move the model, features and graphs "
+                               "to a CUDA device (B200).")
+        if g.device != node_feats.device:
+            raise RuntimeError(f"graph is on {g.device} but features are on {node_feats.device}; call g.to(device)")
+        if node_feats.shape[0] != g.num_nodes() or edge_feats.shape[0] != g.num_edges():
+            raise RuntimeError("feature rows do not match the graph: "
+                               f"{tuple(node_feats.shape)} nodes vs {g.num_nodes()}, "
+                               f"{tuple(edge_feats.shape)} edges vs {g.num_edges()}")
+        cfg = _Cfg()
+        cfg.index = g.index
+        cfg.residual = bool(self.residual)
+        cfg.need_edge_out = bool(_need_edge_out)
+        cfg.bn_nodes, cfg.bn_edges = self.bn_nodes, self.bn_edges
+        cfg.n_aux = cfg.e_aux = None
+        if self.norm_kind == "layernorm":
+            cfg.norm_nodes = cfg.norm_edges = NORM_LAYER
+            cfg.ln_eps = float(self.bn_nodes.eps)
+        else:
+            use_batch_stats = self.training or not self.bn_nodes.track_running_stats
+            cfg.norm_nodes = cfg.norm_edges = NORM_STATS if use_batch_stats else NORM_AFFINE
+            cfg.ln_eps = 1e-5
+        x, y = _EdgeGatedConvFn.apply(
+            cfg, node_feats, edge_feats,
+            self.src_gate.weight, self.src_gate.bias, self.dst_gate.weight, self.dst_gate.bias,
+            self.edge_gate.weight, self.edge_gate.bias, self.src_update.weight, self.src_update.bias,
+            self.dst_update.weight, self.dst_update.bias,
+            self.bn_nodes.weight, self.bn_nodes.bias, self.bn_edges.weight, self.bn_edges.bias)
+        return x, (y if _need_edge_out else None)
+
+
+class ALIGNNConvBase(nn.Module):
+    """Line graph update (alignn/models/alignn.py:132-167): node_update on g, edge_update on L(g)."""
+
+    conv_cls = None  # set by subclasses
+
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__()
+        self.node_update = self.conv_cls(in_features, out_features)
+        self.edge_update = self.conv_cls(out_features, out_features)
+
+    def forward(self, g, lg, x, y, z, _need_z_out: bool = True):
+        g, lg = as_graph(g), as_graph(lg)
+        x, m = self.node_update(g, x, y)
+        # L(g) node i == g edge i: bond features m are the node features of the line graph
+        y, z = self.edge_update(lg, m, z, _need_edge_out=_need_z_out)
+        return x, y, z

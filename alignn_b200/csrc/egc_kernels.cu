@@ -1,0 +1,668 @@
+// Edge-gated graph convolution: gather / gate / segment-reduce / norm kernels, forward and
+// backward, fp32, sm_100a.  One warp owns one destination node (one CSR segment): it walks the
+// node's in-edges in sorted order, gathers the source rows by edge index, and reduces the gated
+// messages in registers -- no atomics, deterministic, every global access a coalesced row.
+//
+// Reference math: alignn/models/alignn.py:98-127.  P is the [Nn,4d] node
+// projection in the layout documented in include/alignn_b200.h: [e_src | Bh | e_dst | src_update].
+#include "common.cuh"
+#include "alignn_b200.h"
+
+namespace alignn {
+
+struct NormVecs {  // pointers to per-channel vectors, meaning depends on the norm mode
+  const float* w; const float* b; const float* mean; const float* rstd; const float* c1; const float* c2;
+};
+
+// u = pre-activation after the norm; returns silu(u)
+__device__ __forceinline__ float silu_(float u) { return u * sigmoidf_(u); }
+__device__ __forceinline__ float dsilu_(float u) { float s = sigmoidf_(u); return s * (1.f + u * (1.f - s)); }
+
+// =============================================================================================
+// Forward
+// =============================================================================================
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+egc_forward_kernel(alignn_b200_egc_fwd_args a) {
+  using C = RowCfg<D>;
+  constexpr int V = C::VPL;
+  __shared__ float red[kWarpsPerBlock * D];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  const bool train = a.M != nullptr;
+
+  float nw[V], nb[V], ew[V], eb[V];
+  ld_vec<D>(nw, a.n_w, lane); ld_vec<D>(nb, a.n_b, lane);
+  ld_vec<D>(ew, a.e_w, lane); ld_vec<D>(eb, a.e_b, lane);
+  float st[4][V];  // STATS mode: {sum m, sum m^2, sum x', sum x'^2}
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int i = 0; i < V; ++i) st[q][i] = 0.f;
+
+  for (int64_t v = warp0; v < a.Nn; v += nwarps) {
+    const int p0 = a.in_ptr[v], p1 = a.in_ptr[v + 1];
+    float bv[V], accS[V], accSh[V];
+    ld_row<D, false>(bv, a.P + v * 4 * D + 2 * D, lane);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { accS[i] = 0.f; accSh[i] = 0.f; }
+
+    for (int base = p0; base < p1; base += 32) {
+      const int cnt = min(32, p1 - base);
+      int my_e = 0, my_s = 0;
+      if (lane < cnt) {
+        my_e = a.in_eid ? a.in_eid[base + lane] : base + lane;
+        my_s = a.src[my_e];
+      }
+      for (int i = 0; i < cnt; ++i) {
+        const int64_t e = __shfl_sync(0xffffffffu, my_e, i);
+        const int64_t s = __shfl_sync(0xffffffffu, my_s, i);
+        float g[V], av[V], cv[V], m[V];
+        ld_row<D, true>(g, a.G + e * D, lane);
+        ld_row<D, false>(av, a.P + s * 4 * D, lane);
+        ld_row<D, false>(cv, a.P + s * 4 * D + D, lane);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          m[k] = av[k] + bv[k] + g[k];
+          const float sg = sigmoidf_(m[k]);
+          accS[k] += sg;
+          accSh[k] += cv[k] * sg;
+        }
+        if (train) st_row<D, true>(a.M + e * D, m, lane);
+        if (a.norm_edges == ALIGNN_NORM_STATS) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) { st[0][k] += m[k]; st[1][k] += m[k] * m[k]; }
+        } else if (a.y_out) {
+          float o[V];
+          if (a.norm_edges == ALIGNN_NORM_LAYER) {
+            float mean, rstd;
+            row_mean_rstd<D>(m, a.ln_eps, mean, rstd);
+#pragma unroll
+            for (int k = 0; k < V; ++k) o[k] = silu_((m[k] - mean) * rstd * ew[k] + eb[k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < V; ++k) o[k] = silu_(m[k] * ew[k] + eb[k]);
+          }
+          if (a.residual) {
+            float yr[V];
+            ld_row<D, true>(yr, a.y + e * D, lane);
+#pragma unroll
+            for (int k = 0; k < V; ++k) o[k] += yr[k];
+          }
+          st_row<D, true>(a.y_out + e * D, o, lane);
+        }
+      }
+    }
+    // ---- node finalize: h = Sh/(S+eps); x' = src_update(x) + h; norm; silu; residual -----------
+    float dv[V], xp[V], h[V];
+    ld_row<D, false>(dv, a.P + v * 4 * D + 3 * D, lane);
+#pragma unroll
+    for (int k = 0; k < V; ++k) { h[k] = accSh[k] / (accS[k] + a.gate_eps); xp[k] = dv[k] + h[k]; }
+    if (train) {
+      st_row<D, false>(a.XP + v * D, xp, lane);
+      st_row<D, false>(a.S + v * D, accS, lane);
+      st_row<D, false>(a.H + v * D, h, lane);
+    }
+    if (a.norm_nodes == ALIGNN_NORM_STATS) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) { st[2][k] += xp[k]; st[3][k] += xp[k] * xp[k]; }
+    } else {
+      float o[V];
+      if (a.norm_nodes == ALIGNN_NORM_LAYER) {
+        float mean, rstd;
+        row_mean_rstd<D>(xp, a.ln_eps, mean, rstd);
+#pragma unroll
+        for (int k = 0; k < V; ++k) o[k] = silu_((xp[k] - mean) * rstd * nw[k] + nb[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) o[k] = silu_(xp[k] * nw[k] + nb[k]);
+      }
+      if (a.residual) {
+        float xr[V];
+        ld_row<D, false>(xr, a.x + v * D, lane);
+#pragma unroll
+        for (int k = 0; k < V; ++k) o[k] += xr[k];
+      }
+      st_row<D, false>(a.x_out + v * D, o, lane);
+    }
+  }
+  if (a.partials) block_reduce_to_partials<D, 4>(st, a.partials + (int64_t)blockIdx.x * 4 * D, red);
+}
+
+// =============================================================================================
+// Backward, destination-keyed pass: node-norm backward, per-edge gate backward, edge-norm
+// backward, GM = dL/dm, GP[:, 2d:3d] = sum over in-edges (dL/d e_dst), GP[:, 3d:4d] = dL/dx'.
+// partials row: {sum gu_e*xhat_e, sum gu_e, sum gu_n*xhat_n, sum gu_n, sum gD, sum gB}
+// =============================================================================================
+template <int D>
+__device__ __forceinline__ void norm_backward_row(const float (&r)[RowCfg<D>::VPL], const float (&go)[RowCfg<D>::VPL],
+                                                  int mode, float ln_eps,
+                                                  const float (&w)[RowCfg<D>::VPL], const float (&b)[RowCfg<D>::VPL],
+                                                  const float (&mu)[RowCfg<D>::VPL], const float (&rs)[RowCfg<D>::VPL],
+                                                  const float (&c1)[RowCfg<D>::VPL], const float (&c2)[RowCfg<D>::VPL],
+                                                  float (&gr)[RowCfg<D>::VPL], float (&acc_gw)[RowCfg<D>::VPL],
+                                                  float (&acc_gb)[RowCfg<D>::VPL]) {
+  constexpr int V = RowCfg<D>::VPL;
+  if (mode == ALIGNN_NORM_LAYER) {
+    float mean, rstd;
+    row_mean_rstd<D>(r, ln_eps, mean, rstd);
+    float xh[V], gxh[V], sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      xh[k] = (r[k] - mean) * rstd;
+      const float gu = go[k] * dsilu_(xh[k] * w[k] + b[k]);
+      acc_gw[k] += gu * xh[k];
+      acc_gb[k] += gu;
+      gxh[k] = gu * w[k];
+      sa += gxh[k];
+      sb += gxh[k] * xh[k];
+    }
+    sa = warp_sum(sa) * (1.f / D);
+    sb = warp_sum(sb) * (1.f / D);
+#pragma unroll
+    for (int k = 0; k < V; ++k) gr[k] = rstd * (gxh[k] - sa - xh[k] * sb);
+  } else {
+    // w = scale, b = shift; xhat = (r - mean_c) * rstd_c
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float gu = go[k] * dsilu_(r[k] * w[k] + b[k]);
+      const float xh = (r[k] - mu[k]) * rs[k];
+      acc_gw[k] += gu * xh;
+      acc_gb[k] += gu;
+      gr[k] = (mode == ALIGNN_NORM_STATS) ? w[k] * (gu - c1[k] - xh * c2[k]) : w[k] * gu;
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+egc_backward_dst_kernel(alignn_b200_egc_bwd_args a) {
+  using C = RowCfg<D>;
+  constexpr int V = C::VPL;
+  __shared__ float red[kWarpsPerBlock * D];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+
+  float acc[6][V];
+#pragma unroll
+  for (int q = 0; q < 6; ++q)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[q][i] = 0.f;
+
+  for (int64_t v = warp0; v < a.Nn; v += nwarps) {
+    float gsh[V], gs[V];
+    {  // node side
+      float nw[V], nb[V], nmu[V], nrs[V], nc1[V], nc2[V];
+      ld_vec<D>(nw, a.n_w, lane); ld_vec<D>(nb, a.n_b, lane);
+      ld_vec<D>(nmu, a.n_mean, lane); ld_vec<D>(nrs, a.n_rstd, lane);
+      ld_vec<D>(nc1, a.n_c1, lane); ld_vec<D>(nc2, a.n_c2, lane);
+      float xp[V], go[V], gxp[V], sv[V], hv[V];
+      ld_row<D, false>(xp, a.XP + v * D, lane);
+      ld_row<D, false>(go, a.gx_out + v * D, lane);
+      norm_backward_row<D>(xp, go, a.norm_nodes, a.ln_eps, nw, nb, nmu, nrs, nc1, nc2, gxp, acc[2], acc[3]);
+      st_row<D, false>(a.GP + v * 4 * D + 3 * D, gxp, lane);
+      ld_row<D, false>(sv, a.S + v * D, lane);
+      ld_row<D, false>(hv, a.H + v * D, lane);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float inv = 1.f / (sv[k] + a.gate_eps);
+        gsh[k] = gxp[k] * inv;
+        gs[k] = -gxp[k] * hv[k] * inv;
+        acc[4][k] += gxp[k];
+      }
+      st_row<D, false>(a.GSh + v * D, gsh, lane);
+    }
+    float ew[V], eb[V], emu[V], ers[V], ec1[V], ec2[V];
+    ld_vec<D>(ew, a.e_w, lane); ld_vec<D>(eb, a.e_b, lane);
+    ld_vec<D>(emu, a.e_mean, lane); ld_vec<D>(ers, a.e_rstd, lane);
+    ld_vec<D>(ec1, a.e_c1, lane); ld_vec<D>(ec2, a.e_c2, lane);
+    float accB[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) accB[k] = 0.f;
+    const int p0 = a.in_ptr[v], p1 = a.in_ptr[v + 1];
+    for (int base = p0; base < p1; base += 32) {
+      const int cnt = min(32, p1 - base);
+      int my_e = 0, my_s = 0;
+      if (lane < cnt) {
+        my_e = a.in_eid ? a.in_eid[base + lane] : base + lane;
+        my_s = a.src[my_e];
+      }
+      for (int i = 0; i < cnt; ++i) {
+        const int64_t e = __shfl_sync(0xffffffffu, my_e, i);
+        const int64_t s = __shfl_sync(0xffffffffu, my_s, i);
+        float m[V], cv[V], gm[V];
+        ld_row<D, true>(m, a.M + e * D, lane);
+        ld_row<D, false>(cv, a.P + s * 4 * D + D, lane);
+        if (a.gy_out) {
+          float go[V];
+          ld_row<D, true>(go, a.gy_out + e * D, lane);
+          norm_backward_row<D>(m, go, a.norm_edges, a.ln_eps, ew, eb, emu, ers, ec1, ec2, gm, acc[0], acc[1]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < V; ++k) gm[k] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float sg = sigmoidf_(m[k]);
+          gm[k] += (gsh[k] * cv[k] + gs[k]) * sg * (1.f - sg);
+          accB[k] += gm[k];
+        }
+        st_row<D, false>(a.GM + e * D, gm, lane);   // re-read by the src-keyed pass and the GEMMs
+      }
+    }
+    st_row<D, false>(a.GP + v * 4 * D + 2 * D, accB, lane);
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[5][k] += accB[k];
+  }
+  if (a.partials) block_reduce_to_partials<D, 6>(acc, a.partials + (int64_t)blockIdx.x * 6 * D, red);
+}
+
+// =============================================================================================
+// Backward, source-keyed pass (out-CSR): GP[:, 0:d] = sum over out-edges of GM (dL/d e_src),
+// GP[:, d:2d] = sum over out-edges of GSh[dst] * sigma (dL/d Bh).
+// partials row: {sum gA, sum gC}
+// =============================================================================================
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+egc_backward_src_kernel(alignn_b200_egc_bwd_args a, float* __restrict__ partials_src) {
+  using C = RowCfg<D>;
+  constexpr int V = C::VPL;
+  __shared__ float red[kWarpsPerBlock * D];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  float acc[2][V];
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[q][i] = 0.f;
+
+  for (int64_t u = warp0; u < a.Nn; u += nwarps) {
+    float accA[V], accC[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { accA[k] = 0.f; accC[k] = 0.f; }
+    const int p0 = a.out_ptr[u], p1 = a.out_ptr[u + 1];
+    for (int base = p0; base < p1; base += 32) {
+      const int cnt = min(32, p1 - base);
+      int my_e = 0, my_t = 0;
+      if (lane < cnt) {
+        my_e = a.out_eid[base + lane];
+        my_t = a.dst[my_e];
+      }
+      for (int i = 0; i < cnt; ++i) {
+        const int64_t e = __shfl_sync(0xffffffffu, my_e, i);
+        const int64_t t = __shfl_sync(0xffffffffu, my_t, i);
+        float gm[V], m[V], gsh[V];
+        ld_row<D, false>(gm, a.GM + e * D, lane);
+        ld_row<D, true>(m, a.M + e * D, lane);
+        ld_row<D, false>(gsh, a.GSh + t * D, lane);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          accA[k] += gm[k];
+          accC[k] += gsh[k] * sigmoidf_(m[k]);
+        }
+      }
+    }
+    st_row<D, false>(a.GP + u * 4 * D, accA, lane);
+    st_row<D, false>(a.GP + u * 4 * D + D, accC, lane);
+#pragma unroll
+    for (int k = 0; k < V; ++k) { acc[0][k] += accA[k]; acc[1][k] += accC[k]; }
+  }
+  if (partials_src) block_reduce_to_partials<D, 2>(acc, partials_src + (int64_t)blockIdx.x * 2 * D, red);
+}
+
+// =============================================================================================
+// BatchNorm train-mode helpers
+// =============================================================================================
+// one block of d threads; fp64 accumulation over the per-block partial rows
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int rows, int stride, int which, double count,
+                                   int d, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                                   float* mean_out, float* rstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  double s = 0.0, q = 0.0;
+  const float* p = partials + (size_t)which * 2 * d + c;
+  for (int r = 0; r < rows; ++r) {
+    s += (double)p[(size_t)r * stride];
+    q += (double)p[(size_t)r * stride + d];
+  }
+  const double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale[c] = g * rstd;
+  shift[c] = b - (float)mean * g * rstd;
+  mean_out[c] = (float)mean;
+  rstd_out[c] = rstd;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+affine_silu_residual_kernel(const float* __restrict__ R, const float* __restrict__ res, const float* __restrict__ scale,
+                            const float* __restrict__ shift, float* __restrict__ out, int64_t n) {
+  constexpr int V = RowCfg<D>::VPL;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  float sc[V], sh[V];
+  ld_vec<D>(sc, scale, lane); ld_vec<D>(sh, shift, lane);
+  for (int64_t r = warp0; r < n; r += nwarps) {
+    float v[V], o[V];
+    ld_row<D, true>(v, R + r * D, lane);
+#pragma unroll
+    for (int k = 0; k < V; ++k) o[k] = silu_(v[k] * sc[k] + sh[k]);
+    if (res) {
+      float y[V];
+      ld_row<D, true>(y, res + r * D, lane);
+#pragma unroll
+      for (int k = 0; k < V; ++k) o[k] += y[k];
+    }
+    st_row<D, true>(out + r * D, o, lane);
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+bn_backward_reduce_kernel(const float* __restrict__ R, const float* __restrict__ g_out, const float* __restrict__ scale,
+                          const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
+                          int64_t n, float* __restrict__ partials) {
+  constexpr int V = RowCfg<D>::VPL;
+  __shared__ float red[kWarpsPerBlock * D];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  float sc[V], sh[V], mu[V], rs[V], acc[2][V];
+  ld_vec<D>(sc, scale, lane); ld_vec<D>(sh, shift, lane); ld_vec<D>(mu, mean, lane); ld_vec<D>(rs, rstd, lane);
+#pragma unroll
+  for (int k = 0; k < V; ++k) { acc[0][k] = 0.f; acc[1][k] = 0.f; }
+  for (int64_t r = warp0; r < n; r += nwarps) {
+    float v[V], g[V];
+    ld_row<D, false>(v, R + r * D, lane);
+    ld_row<D, false>(g, g_out + r * D, lane);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float gu = g[k] * dsilu_(v[k] * sc[k] + sh[k]);
+      acc[0][k] += gu;
+      acc[1][k] += gu * (v[k] - mu[k]) * rs[k];
+    }
+  }
+  block_reduce_to_partials<D, 2>(acc, partials + (int64_t)blockIdx.x * 2 * D, red);
+}
+
+// out[c] = alpha * sum_r a[r*stride + c]; one thread per column, rows summed in fp64 in a fixed order.
+// Used on per-block partial buffers (rows <= kMaxBlocks), so the serial row loop is short.
+__global__ void colsum_kernel(const float* __restrict__ a, int64_t rows, int cols, int64_t stride, float alpha,
+                              float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double s = 0.0;
+  for (int64_t r = 0; r < rows; ++r) s += (double)a[r * stride + c];
+  out[c] = alpha * (float)s;
+}
+
+// =============================================================================================
+// Gather / segment-sum primitive (DGL u_mul_e -> sum and copy_e -> sum in one pass)
+// =============================================================================================
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+gather_segment_sum_kernel(const float* __restrict__ Bh, const float* __restrict__ sigma, const int32_t* __restrict__ src,
+                          const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_eid, int64_t Nn,
+                          float* __restrict__ Sh, float* __restrict__ S) {
+  constexpr int V = RowCfg<D>::VPL;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t v = warp0; v < Nn; v += nwarps) {
+    float accS[V], accSh[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { accS[k] = 0.f; accSh[k] = 0.f; }
+    const int p0 = in_ptr[v], p1 = in_ptr[v + 1];
+    for (int base = p0; base < p1; base += 32) {
+      const int cnt = min(32, p1 - base);
+      int my_e = 0, my_s = 0;
+      if (lane < cnt) {
+        my_e = in_eid ? in_eid[base + lane] : base + lane;
+        my_s = src[my_e];
+      }
+      int i = 0;
+      for (; i + 1 < cnt; i += 2) {   // two edges in flight per warp
+        const int64_t e0 = __shfl_sync(0xffffffffu, my_e, i), s0 = __shfl_sync(0xffffffffu, my_s, i);
+        const int64_t e1 = __shfl_sync(0xffffffffu, my_e, i + 1), s1 = __shfl_sync(0xffffffffu, my_s, i + 1);
+        float g0[V], b0[V], g1[V], b1[V];
+        ld_row<D, true>(g0, sigma + e0 * D, lane);
+        ld_row<D, true>(g1, sigma + e1 * D, lane);
+        ld_row<D, false>(b0, Bh + s0 * D, lane);
+        ld_row<D, false>(b1, Bh + s1 * D, lane);
+#pragma unroll
+        for (int k = 0; k < V; ++k) { accS[k] += g0[k]; accSh[k] += b0[k] * g0[k]; }
+#pragma unroll
+        for (int k = 0; k < V; ++k) { accS[k] += g1[k]; accSh[k] += b1[k] * g1[k]; }
+      }
+      if (i < cnt) {
+        const int64_t e0 = __shfl_sync(0xffffffffu, my_e, i), s0 = __shfl_sync(0xffffffffu, my_s, i);
+        float g0[V], b0[V];
+        ld_row<D, true>(g0, sigma + e0 * D, lane);
+        ld_row<D, false>(b0, Bh + s0 * D, lane);
+#pragma unroll
+        for (int k = 0; k < V; ++k) { accS[k] += g0[k]; accSh[k] += b0[k] * g0[k]; }
+      }
+    }
+    st_row<D, true>(Sh + v * D, accSh, lane);
+    st_row<D, true>(S + v * D, accS, lane);
+  }
+}
+
+// =============================================================================================
+// Per-graph mean pooling over node rows and its backward (block per graph)
+// =============================================================================================
+__global__ void segment_mean_kernel(const float* __restrict__ x, const int32_t* __restrict__ gptr, int d,
+                                    float* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int r0 = gptr[b], r1 = gptr[b + 1];
+  const float inv = r1 > r0 ? 1.f / (float)(r1 - r0) : 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += x[(size_t)r * d + c];
+    out[(size_t)b * d + c] = s * inv;
+  }
+}
+
+__global__ void segment_mean_backward_kernel(const float* __restrict__ g_out, const int32_t* __restrict__ gptr, int d,
+                                             float* __restrict__ gx) {
+  const int b = blockIdx.x;
+  const int r0 = gptr[b], r1 = gptr[b + 1];
+  const float inv = r1 > r0 ? 1.f / (float)(r1 - r0) : 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const float g = g_out[(size_t)b * d + c] * inv;
+    for (int r = r0; r < r1; ++r) gx[(size_t)r * d + c] = g;
+  }
+}
+
+}  // namespace alignn
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+#include <atomic>
+
+namespace {
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_last_cuda_error{0};
+
+inline int check_launch() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_cuda_error.store((int)e); return ALIGNN_ERR_CUDA; }
+  return ALIGNN_OK;
+}
+inline bool supported_d(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
+inline int grid_for_rows(int64_t n) {
+  int64_t b = (n + alignn::kWarpsPerBlock - 1) / alignn::kWarpsPerBlock;
+  if (b < 1) b = 1;
+  if (b > alignn::kMaxBlocks) b = alignn::kMaxBlocks;
+  return (int)b;
+}
+inline bool norm_ok(int m) { return m == ALIGNN_NORM_LAYER || m == ALIGNN_NORM_AFFINE || m == ALIGNN_NORM_STATS; }
+}  // namespace
+
+#define DISPATCH_D(d, ...)                         \
+  switch (d) {                                     \
+    case 32: { constexpr int D = 32; __VA_ARGS__; break; }   \
+    case 64: { constexpr int D = 64; __VA_ARGS__; break; }   \
+    case 128: { constexpr int D = 128; __VA_ARGS__; break; } \
+    case 256: { constexpr int D = 256; __VA_ARGS__; break; } \
+    default: return ALIGNN_ERR_UNSUPPORTED_D;      \
+  }
+
+extern "C" {
+
+int alignn_b200_version(void) { return ALIGNN_B200_VERSION; }
+
+const char* alignn_b200_strerror(int s) {
+  switch (s) {
+    case ALIGNN_OK: return "ok";
+    case ALIGNN_ERR_BAD_ARG: return "bad argument (NULL pointer, negative size or invalid flag)";
+    case ALIGNN_ERR_UNSUPPORTED_D: return "unsupported feature width d (supported: 32, 64, 128, 256)";
+    case ALIGNN_ERR_STRUCT_SIZE: return "argument struct size mismatch between caller and library";
+    case ALIGNN_ERR_CUDA: return "CUDA runtime error (see alignn_b200_last_cuda_error)";
+    case ALIGNN_ERR_WORKSPACE: return "workspace too small";
+    default: return "unknown status";
+  }
+}
+
+int alignn_b200_last_cuda_error(void) { return g_last_cuda_error.load(); }
+uint64_t alignn_b200_launch_count(void) { return g_launches.load(); }
+
+int alignn_b200_egc_partial_rows(int64_t Nn, int d) { (void)d; return grid_for_rows(Nn); }
+
+int alignn_b200_egc_forward(const alignn_b200_egc_fwd_args* a) {
+  if (!a) return ALIGNN_ERR_BAD_ARG;
+  if (a->struct_size != sizeof(*a)) return ALIGNN_ERR_STRUCT_SIZE;
+  if (!supported_d(a->d)) return ALIGNN_ERR_UNSUPPORTED_D;
+  if (a->Nn < 0 || a->Ne < 0 || !norm_ok(a->norm_nodes) || !norm_ok(a->norm_edges)) return ALIGNN_ERR_BAD_ARG;
+  if (a->Nn == 0) return ALIGNN_OK;
+  if (!a->P || !a->in_ptr || (a->Ne > 0 && (!a->G || !a->src))) return ALIGNN_ERR_BAD_ARG;
+  if (a->norm_nodes != ALIGNN_NORM_STATS && (!a->x_out || !a->n_w || !a->n_b)) return ALIGNN_ERR_BAD_ARG;
+  if (a->norm_edges != ALIGNN_NORM_STATS && a->y_out && (!a->e_w || !a->e_b)) return ALIGNN_ERR_BAD_ARG;
+  if (a->residual && ((a->norm_nodes != ALIGNN_NORM_STATS && !a->x) ||
+                      (a->norm_edges != ALIGNN_NORM_STATS && a->y_out && !a->y))) return ALIGNN_ERR_BAD_ARG;
+  if ((a->norm_nodes == ALIGNN_NORM_STATS || a->norm_edges == ALIGNN_NORM_STATS) && !a->partials) return ALIGNN_ERR_BAD_ARG;
+  if ((a->norm_nodes == ALIGNN_NORM_STATS || a->norm_edges == ALIGNN_NORM_STATS) && !a->M) return ALIGNN_ERR_BAD_ARG;
+  if (a->M && (!a->XP || !a->S || !a->H)) return ALIGNN_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)a->stream;
+  const int grid = grid_for_rows(a->Nn);
+  DISPATCH_D(a->d, alignn::egc_forward_kernel<D><<<grid, alignn::kThreads, 0, st>>>(*a));
+  return check_launch();
+}
+
+int alignn_b200_bn_finalize(const float* partials, int partial_rows, int partial_stride, int which, int64_t count, int d,
+                            const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                            float* running_var, float* scale, float* shift, float* mean, float* rstd,
+                            alignn_stream_t stream) {
+  if (!partials || !scale || !shift || !mean || !rstd || partial_rows <= 0 || d <= 0 || count <= 0 ||
+      (which != 0 && which != 1) || ((running_mean == nullptr) != (running_var == nullptr)))
+    return ALIGNN_ERR_BAD_ARG;
+  alignn::bn_finalize_kernel<<<(d + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      partials, partial_rows, partial_stride, which, (double)count, d, gamma, beta, eps, momentum, running_mean,
+      running_var, scale, shift, mean, rstd);
+  return check_launch();
+}
+
+int alignn_b200_affine_silu_residual(const float* R, const float* res, const float* scale, const float* shift, float* out,
+                                     int64_t n, int d, alignn_stream_t stream) {
+  if (!supported_d(d)) return ALIGNN_ERR_UNSUPPORTED_D;
+  if (n < 0 || (n > 0 && (!R || !scale || !shift || !out))) return ALIGNN_ERR_BAD_ARG;
+  if (n == 0) return ALIGNN_OK;
+  const int grid = grid_for_rows(n);
+  DISPATCH_D(d, alignn::affine_silu_residual_kernel<D><<<grid, alignn::kThreads, 0, (cudaStream_t)stream>>>(
+                    R, res, scale, shift, out, n));
+  return check_launch();
+}
+
+int alignn_b200_egc_backward(const alignn_b200_egc_bwd_args* a) {
+  if (!a) return ALIGNN_ERR_BAD_ARG;
+  if (a->struct_size != sizeof(*a)) return ALIGNN_ERR_STRUCT_SIZE;
+  if (!supported_d(a->d)) return ALIGNN_ERR_UNSUPPORTED_D;
+  if (a->Nn < 0 || a->Ne < 0 || !norm_ok(a->norm_nodes) || !norm_ok(a->norm_edges)) return ALIGNN_ERR_BAD_ARG;
+  if (a->Nn == 0) return ALIGNN_OK;
+  if (!a->P || !a->XP || !a->S || !a->H || !a->in_ptr || !a->out_ptr || !a->gx_out || !a->GP || !a->GSh ||
+      !a->n_w || !a->n_b)
+    return ALIGNN_ERR_BAD_ARG;
+  if (a->Ne > 0 && (!a->M || !a->src || !a->dst || !a->out_eid || !a->GM)) return ALIGNN_ERR_BAD_ARG;
+  if (a->norm_nodes != ALIGNN_NORM_LAYER && (!a->n_mean || !a->n_rstd)) return ALIGNN_ERR_BAD_ARG;
+  if (a->norm_nodes == ALIGNN_NORM_STATS && (!a->n_c1 || !a->n_c2)) return ALIGNN_ERR_BAD_ARG;
+  if (a->gy_out) {
+    if (!a->e_w || !a->e_b) return ALIGNN_ERR_BAD_ARG;
+    if (a->norm_edges != ALIGNN_NORM_LAYER && (!a->e_mean || !a->e_rstd)) return ALIGNN_ERR_BAD_ARG;
+    if (a->norm_edges == ALIGNN_NORM_STATS && (!a->e_c1 || !a->e_c2)) return ALIGNN_ERR_BAD_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)a->stream;
+  const int grid = grid_for_rows(a->Nn);
+  DISPATCH_D(a->d, alignn::egc_backward_dst_kernel<D><<<grid, alignn::kThreads, 0, st>>>(*a));
+  int rc = check_launch();
+  if (rc != ALIGNN_OK) return rc;
+  DISPATCH_D(a->d, alignn::egc_backward_src_kernel<D><<<grid, alignn::kThreads, 0, st>>>(*a, a->partials_src));
+  return check_launch();
+}
+
+int alignn_b200_bn_backward_reduce(const float* R, const float* g_out, const float* scale, const float* shift,
+                                   const float* mean, const float* rstd, int64_t n, int d, float* partials,
+                                   int partial_rows, alignn_stream_t stream) {
+  if (!supported_d(d)) return ALIGNN_ERR_UNSUPPORTED_D;
+  if (n <= 0 || !R || !g_out || !scale || !shift || !mean || !rstd || !partials) return ALIGNN_ERR_BAD_ARG;
+  const int grid = grid_for_rows(n);
+  if (partial_rows < grid) return ALIGNN_ERR_WORKSPACE;
+  DISPATCH_D(d, alignn::bn_backward_reduce_kernel<D><<<grid, alignn::kThreads, 0, (cudaStream_t)stream>>>(
+                    R, g_out, scale, shift, mean, rstd, n, partials));
+  return check_launch();
+}
+
+int alignn_b200_colsum(const float* a, int64_t rows, int cols, int64_t stride, float alpha, float* out,
+                       alignn_stream_t stream) {
+  if (!a || !out || rows < 0 || cols <= 0 || stride < cols) return ALIGNN_ERR_BAD_ARG;
+  alignn::colsum_kernel<<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a, rows, cols, stride, alpha, out);
+  return check_launch();
+}
+
+int alignn_b200_gather_segment_sum(const float* Bh, const float* sigma, const int32_t* src, const int32_t* in_ptr,
+                                   const int32_t* in_eid, int64_t Nn, int64_t Ne, int d, float* Sh, float* S,
+                                   alignn_stream_t stream) {
+  if (!supported_d(d)) return ALIGNN_ERR_UNSUPPORTED_D;
+  if (Nn < 0 || Ne < 0) return ALIGNN_ERR_BAD_ARG;
+  if (Nn == 0) return ALIGNN_OK;
+  if (!in_ptr || !Sh || !S || (Ne > 0 && (!Bh || !sigma || !src))) return ALIGNN_ERR_BAD_ARG;
+  int64_t b = (Nn + alignn::kWarpsPerBlock - 1) / alignn::kWarpsPerBlock;
+  const int grid = (int)(b > alignn::kNumSMs * 16 ? alignn::kNumSMs * 16 : b);
+  DISPATCH_D(d, alignn::gather_segment_sum_kernel<D><<<grid, alignn::kThreads, 0, (cudaStream_t)stream>>>(
+                    Bh, sigma, src, in_ptr, in_eid, Nn, Sh, S));
+  return check_launch();
+}
+
+int alignn_b200_segment_mean(const float* x, const int32_t* graph_ptr, int64_t B, int d, float* out,
+                             alignn_stream_t stream) {
+  if (B < 0 || d <= 0) return ALIGNN_ERR_BAD_ARG;
+  if (B == 0) return ALIGNN_OK;
+  if (!x || !graph_ptr || !out) return ALIGNN_ERR_BAD_ARG;
+  alignn::segment_mean_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(x, graph_ptr, d, out);
+  return check_launch();
+}
+
+int alignn_b200_segment_mean_backward(const float* g_out, const int32_t* graph_ptr, int64_t B, int d, float* gx,
+                                      alignn_stream_t stream) {
+  if (B < 0 || d <= 0) return ALIGNN_ERR_BAD_ARG;
+  if (B == 0) return ALIGNN_OK;
+  if (!g_out || !graph_ptr || !gx) return ALIGNN_ERR_BAD_ARG;
+  alignn::segment_mean_backward_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(g_out, graph_ptr, d, gx);
+  return check_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+"""Tensor-level wrappers over the C ABI (include/alignn_b200.h).  Device memory, streams
+and the autograd glue are PyTorch plumbing; all arithmetic of the edge-gated conv stage
+runs in libalignn_b200.so.  Every function raises if the tensors are not fp32/int32 CUDA
+tensors or if the library reports an error -- there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import NORM_AFFINE, NORM_LAYER, NORM_STATS, ptr, require_cuda, stream_ptr  # noqa: F401
+from .graph import EdgeIndex
+
+
+def _check_d(d: int) -> None:
+    if d not in _lib.SUPPORTED_D:
+        raise RuntimeError(f"alignn_b200: unsupported feature width {d}; supported: {_lib.SUPPORTED_D}")
+
+
+def partial_rows(num_nodes: int, d: int) -> int:
+    return int(_lib.load().alignn_b200_egc_partial_rows(num_nodes, d))
+
+
+def egc_forward(ix: EdgeIndex, x, y, G, P, n_w, n_b, e_w, e_b, *, norm_nodes: int, norm_edges: int,
+                residual: bool, save: bool, need_edge_out: bool, gate_eps: float = 1e-6, ln_eps: float = 1e-5):
+    """Everything of EdgeGatedGraphConv.forward after the Linear layers (alignn.py:100-127).
+
+    Returns dict(x_out, y_out, M, XP, S, H, partials)."""
+    lib = _lib.load()
+    Nn, d = x.shape
+    Ne = y.shape[0]
+    _check_d(d)
+    require_cuda(x, y, G, P, n_w, n_b, e_w, e_b, ix.src, ix.in_ptr, ix.in_eid)
+    stats = norm_nodes == NORM_STATS or norm_edges == NORM_STATS
+    save = save or stats
+    dev = x.device
+    new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+    x_out = None if norm_nodes == NORM_STATS else new(Nn, d)
+    y_out = new(Ne, d) if (need_edge_out and norm_edges != NORM_STATS) else None
+    M = new(Ne, d) if save else None
+    XP, S, H = (new(Nn, d), new(Nn, d), new(Nn, d)) if save else (None, None, None)
+    partials = new(partial_rows(Nn, d), 4, d) if stats else None
+    a = _lib.EgcFwdArgs(
+        struct_size=C.sizeof(_lib.EgcFwdArgs), Nn=Nn, Ne=Ne, d=d, norm_nodes=norm_nodes, norm_edges=norm_edges,
+        residual=int(residual), gate_eps=gate_eps, ln_eps=ln_eps,
+        x=ptr(x), y=ptr(y), G=ptr(G), P=ptr(P), src=ptr(ix.src), in_ptr=ptr(ix.in_ptr),
+        in_eid=None if ix.dst_sorted else ptr(ix.in_eid),
+        n_w=ptr(n_w), n_b=ptr(n_b), e_w=ptr(e_w), e_b=ptr(e_b),
+        x_out=ptr(x_out), y_out=ptr(y_out), M=ptr(M), XP=ptr(XP), S=ptr(S), H=ptr(H), partials=ptr(partials),
+        stream=stream_ptr())
+    _lib.check(lib.alignn_b200_egc_forward(C.byref(a)), "alignn_b200_egc_forward")
+    return dict(x_out=x_out, y_out=y_out, M=M, XP=XP, S=S, H=H, partials=partials)
+
+
+def bn_finalize(partials, which: int, count: int, gamma, beta, eps: float, momentum: float,
+                running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor]):
+    """Batch statistics -> (scale, shift, mean, rstd); updates running stats in place."""
+    lib = _lib.load()
+    rows, nq, d = partials.shape
+    require_cuda(partials, gamma, beta, running_mean, running_var)
+    out = torch.empty(4, d, device=partials.device, dtype=torch.float32)
+    _lib.check(lib.alignn_b200_bn_finalize(ptr(partials), rows, nq * d, which, count, d, ptr(gamma), ptr(beta), eps,
+                                            momentum, ptr(running_mean), ptr(running_var), ptr(out[0]), ptr(out[1]),
+                                            ptr(out[2]), ptr(out[3]), stream_ptr()), "alignn_b200_bn_finalize")
+    return out[0], out[1], out[2], out[3]
+
+
+def affine_silu_residual(R, res, scale, shift):
+    lib = _lib.load()
+    n, d = R.shape
+    _check_d(d)
+    require_cuda(R, res, scale, shift)
+    out = torch.empty_like(R)
+    _lib.check(lib.alignn_b200_affine_silu_residual(ptr(R), ptr(res), ptr(scale), ptr(shift), ptr(out), n, d,
+                                                     stream_ptr()), "alignn_b200_affine_silu_residual")
+    return out
+
+
+def colsum(a: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+    """Deterministic fp64-accumulated column sum of a 2-D fp32 tensor (used on partial buffers)."""
+    lib = _lib.load()
+    require_cuda(a)
+    rows, cols = a.shape
+    out = torch.empty(cols, device=a.device, dtype=torch.float32)
+    _lib.check(lib.alignn_b200_colsum(ptr(a), rows, cols, cols, alpha, ptr(out), stream_ptr()), "alignn_b200_colsum")
+    return out
+
+
+def bn_backward_reduce(R, g_out, scale, shift, mean, rstd) -> Tuple[torch.Tensor, torch.Tensor]:
+    """c1 = mean(gu), c2 = mean(gu*xhat) per channel (BatchNorm train-mode backward, pass 1)."""
+    lib = _lib.load()
+    n, d = R.shape
+    _check_d(d)
+    require_cuda(R, g_out, scale, shift, mean, rstd)
+    rows = partial_rows(n, d)
+    partials = torch.empty(rows, 2 * d, device=R.device, dtype=torch.float32)
+    _lib.check(lib.alignn_b200_bn_backward_reduce(ptr(R), ptr(g_out), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), n, d,
+                                                   ptr(partials), rows, stream_ptr()), "alignn_b200_bn_backward_reduce")
+    c = colsum(partials, 1.0 / n)
+    return c[:d], c[d:]
+
+
+def egc_backward(ix: EdgeIndex, P, M, XP, S, H, gx_out, gy_out, n, e, *, norm_nodes: int, norm_edges: int,
+                 gate_eps: float = 1e-6, ln_eps: float = 1e-5):
+    """n / e: dicts with keys w, b, mean, rstd, c1, c2 (entries may be None).
+
+    Returns GM [Ne,d], GP [Nn,4d], vec_dst [6,d], vec_src [2,d] (column sums of the partials)."""
+    lib = _lib.load()
+    Nn, d = XP.shape
+    Ne = M.shape[0]
+    _check_d(d)
+    require_cuda(P, M, XP, S, H, gx_out, gy_out, ix.src, ix.dst, ix.in_ptr, ix.in_eid, ix.out_ptr, ix.out_eid,
+                 *[t for dct in (n, e) for t in dct.values()])
+    dev = XP.device
+    new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+    GM, GP, GSh = new(Ne, d), new(Nn, 4 * d), new(Nn, d)
+    rows = partial_rows(Nn, d)
+    part, part_src = new(rows, 6 * d), new(rows, 2 * d)
+    g = lambda dct, k: ptr(dct.get(k))  # noqa: E731
+    a = _lib.EgcBwdArgs(
+        struct_size=C.sizeof(_lib.EgcBwdArgs), Nn=Nn, Ne=Ne, d=d, norm_nodes=norm_nodes, norm_edges=norm_edges,
+        gate_eps=gate_eps, ln_eps=ln_eps, P=ptr(P), M=ptr(M), XP=ptr(XP), S=ptr(S), H=ptr(H),
+        src=ptr(ix.src), dst=ptr(ix.dst), in_ptr=ptr(ix.in_ptr), in_eid=None if ix.dst_sorted else ptr(ix.in_eid),
+        out_ptr=ptr(ix.out_ptr), out_eid=ptr(ix.out_eid),
+        n_w=g(n, "w"), n_b=g(n, "b"), n_mean=g(n, "mean"), n_rstd=g(n, "rstd"),
+        e_w=g(e, "w"), e_b=g(e, "b"), e_mean=g(e, "mean"), e_rstd=g(e, "rstd"),
+        n_c1=g(n, "c1"), n_c2=g(n, "c2"), e_c1=g(e, "c1"), e_c2=g(e, "c2"),
+        gx_out=ptr(gx_out), gy_out=ptr(gy_out), GM=ptr(GM), GP=ptr(GP), GSh=ptr(GSh),
+        partials=ptr(part), partials_src=ptr(part_src), stream=stream_ptr())
+    _lib.check(lib.alignn_b200_egc_backward(C.byref(a)), "alignn_b200_egc_backward")
+    return GM, GP, colsum(part).view(6, d), colsum(part_src).view(2, d)
+
+
+def gather_segment_sum(ix: EdgeIndex, Bh, sigma):
+    """Sh[v] = sum_{e->v} Bh[src e] * sigma[e];  S[v] = sum_{e->v} sigma[e]  (alignn.py:105-108)."""
+    lib = _lib.load()
+    Nn, d = Bh.shape
+    Ne = sigma.shape[0]
+    _check_d(d)
+    require_cuda(Bh, sigma, ix.src, ix.in_ptr, ix.in_eid)
+    Sh, S = torch.empty_like(Bh), torch.empty_like(Bh)
+    _lib.check(lib.alignn_b200_gather_segment_sum(ptr(Bh), ptr(sigma), ptr(ix.src), ptr(ix.in_ptr),
+                                                   None if ix.dst_sorted else ptr(ix.in_eid), Nn, Ne, d, ptr(Sh), ptr(S),
+                                                   stream_ptr()), "alignn_b200_gather_segment_sum")
+    return Sh, S
+
+
+class _SegmentMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gptr):
+        lib = _lib.load()
+        require_cuda(x, gptr)
+        B, d = gptr.numel() - 1, x.shape[1]
+        out = torch.empty(B, d, device=x.device, dtype=torch.float32)
+        _lib.check(lib.alignn_b200_segment_mean(ptr(x), ptr(gptr), B, d, ptr(out), stream_ptr()), "alignn_b200_segment_mean")
+        ctx.save_for_backward(gptr)
+        ctx.n = x.shape[0]
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        (gptr,) = ctx.saved_tensors
+        g_out = g_out.contiguous()
+        B, d = g_out.shape
+        gx = torch.empty(ctx.n, d, device=g_out.device, dtype=torch.float32)
+        _lib.check(lib.alignn_b200_segment_mean_backward(ptr(g_out), ptr(gptr), B, d, ptr(gx), stream_ptr()),
+                   "alignn_b200_segment_mean_backward")
+        return gx, None
+
+
+def segment_mean(x: torch.Tensor, graph_ptr: torch.Tensor) -> torch.Tensor:
+    """Per-graph mean over node rows (dgl.nn.AvgPooling, alignn.py:325)."""
+    return _SegmentMean.apply(x.contiguous(), graph_ptr)

@@ -1,0 +1,197 @@
+/*
+ * alignn_b200.h -- C ABI of libalignn_b200.so: the B200 (sm_100a) edge-gated graph
+ * convolution hot path of ALIGNN.
+ *
+ * Drop-in boundary.  The reference (usnistgov/alignn, 100 % Python) reaches its device
+ * code through DGL's message-passing dispatch and ATen ops inside
+ *     EdgeGatedGraphConv.forward      alignn/models/alignn.py:78-129
+ *                                     (LayerNorm twin alignn/models/alignn_atomwise.py:157-208)
+ * Each entry point below replaces a group of those call sites; the reference-side binding a
+ * maintainer would add is the ctypes stub shown in INTEGRATION.md (and shipped as
+ * alignn_b200/_lib.py).
+ *
+ * Conventions
+ *   - Only POD crosses the boundary: device pointers, sizes, flags, a CUDA stream handle.
+ *   - Ownership: the caller allocates every buffer (inputs, outputs, workspaces).  The library
+ *     never allocates, frees, or retains a pointer past return.
+ *   - Every call only ENQUEUES work on `stream` (no synchronisation, no host reads of device
+ *     memory) and is re-entrant; one process per GPU.
+ *   - Return value: 0 on success, a negative alignn_b200_status otherwise; nothing throws.
+ *   - All feature matrices are fp32, row-major, contiguous, rows 16-byte aligned.
+ *     All index arrays are int32.  `d` (features per row) must be one of 32, 64, 128, 256.
+ *   - Results do not depend on launch geometry: no floating-point atomics anywhere.
+ *
+ * Node-projection layout.  `P` is the [Nn, 4d] output of the four node Linear layers, column
+ * blocks in this order (chosen so that the per-edge source gather is one contiguous 2d chunk):
+ *     P[:, 0:d]   = src_gate(x)     (alignn.py:98,  "e_src")
+ *     P[:, d:2d]  = dst_update(x)   (alignn.py:104, "Bh")
+ *     P[:, 2d:3d] = dst_gate(x)     (alignn.py:99,  "e_dst")
+ *     P[:, 3d:4d] = src_update(x)   (alignn.py:110)
+ * `GP` (its gradient) uses the same layout.
+ *
+ * Sorted-CSR edge index (int32): in_ptr[Nn+1] / in_eid[Ne] = edge ids stably sorted by
+ * destination; out_ptr[Nn+1] / out_eid[Ne] = stably sorted by source.  in_eid may be NULL when
+ * the edge list itself is destination-sorted (identity permutation).
+ */
+#ifndef ALIGNN_B200_H
+#define ALIGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALIGNN_B200_VERSION 100
+
+typedef enum {
+  ALIGNN_OK = 0,
+  ALIGNN_ERR_BAD_ARG = -1,        /* NULL where a pointer is required, negative size, bad flag */
+  ALIGNN_ERR_UNSUPPORTED_D = -2,  /* d not in {32, 64, 128, 256} */
+  ALIGNN_ERR_STRUCT_SIZE = -3,    /* args->struct_size != sizeof(args): header/binding mismatch */
+  ALIGNN_ERR_CUDA = -4,           /* a CUDA runtime call failed; see alignn_b200_last_cuda_error */
+  ALIGNN_ERR_WORKSPACE = -5       /* workspace too small */
+} alignn_b200_status;
+
+/* How the norm after the gate is applied (alignn.py:122-123). */
+typedef enum {
+  ALIGNN_NORM_LAYER = 0,   /* LayerNorm(d), eps; gamma/beta           (alignn_atomwise.py:151,155) */
+  ALIGNN_NORM_AFFINE = 1,  /* per-channel scale/shift: BatchNorm1d in eval mode (alignn.py:72,76) */
+  ALIGNN_NORM_STATS = 2    /* BatchNorm1d in train mode: emit pre-norm rows + per-channel partial
+                              sums; finish with bn_finalize + bn_apply */
+} alignn_b200_norm;
+
+typedef void* alignn_stream_t; /* a cudaStream_t */
+
+int alignn_b200_version(void);
+const char* alignn_b200_strerror(int status);
+int alignn_b200_last_cuda_error(void);      /* cudaError_t of the last failed runtime call */
+uint64_t alignn_b200_launch_count(void);    /* kernels launched by this library so far */
+
+/* Rows of per-block column partials the egc kernels write: grid size they will use. */
+int alignn_b200_egc_partial_rows(int64_t Nn, int d);
+
+/* ------------------------------------------------------------------------------------------
+ * Forward of one EdgeGatedGraphConv, everything after the Linear layers
+ * (replaces alignn.py:100-127: apply_edges(u_add_v), sigmoid, update_all(u_mul_e,sum),
+ *  update_all(copy_e,sum), the division, both norms, SiLU and the residuals).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  size_t struct_size;
+  int64_t Nn, Ne;
+  int32_t d;
+  int32_t norm_nodes, norm_edges; /* alignn_b200_norm */
+  int32_t residual;               /* alignn.py:125 */
+  float gate_eps;                 /* 1e-6, alignn.py:109 */
+  float ln_eps;                   /* LayerNorm eps */
+  /* inputs */
+  const float* x;       /* [Nn,d] node_feats */
+  const float* y;       /* [Ne,d] edge_feats (residual input) */
+  const float* G;       /* [Ne,d] edge_gate(y) = y W_eg^T + b_eg  (alignn.py:101) */
+  const float* P;       /* [Nn,4d] node projections, layout above */
+  const int32_t* src;   /* [Ne] */
+  const int32_t* in_ptr;  /* [Nn+1] */
+  const int32_t* in_eid;  /* [Ne] or NULL (identity) */
+  /* norm parameters: LAYER -> (gamma, beta); AFFINE -> (scale, shift); STATS -> unused */
+  const float* n_w; const float* n_b;   /* nodes  [d] */
+  const float* e_w; const float* e_b;   /* edges  [d] */
+  /* outputs */
+  float* x_out;   /* [Nn,d]; may be NULL when norm_nodes == STATS */
+  float* y_out;   /* [Ne,d]; NULL = edge output not needed (dead output / STATS) */
+  float* M;       /* [Ne,d] pre-norm gate m (alignn.py:101); NULL in inference */
+  float* XP;      /* [Nn,d] pre-norm node update x' (alignn.py:110); NULL in inference */
+  float* S;       /* [Nn,d] sum_sigma (alignn.py:108); NULL in inference */
+  float* H;       /* [Nn,d] h = sum_sigma_h / (sum_sigma + eps) (alignn.py:109); NULL in inference */
+  /* STATS mode: per-block partial column sums, [partial_rows, 4, d] = {sum m, sum m^2, sum x', sum x'^2} */
+  float* partials;
+  alignn_stream_t stream;
+} alignn_b200_egc_fwd_args;
+
+int alignn_b200_egc_forward(const alignn_b200_egc_fwd_args* args);
+
+/* BatchNorm1d train mode, step 2: reduce partials -> batch mean / biased var (alignn.py:72,76,
+ * torch BatchNorm1d semantics), emit scale = gamma*rstd, shift = beta - mean*scale, save mean and
+ * rstd for backward, and update running_mean / running_var (momentum, unbiased var). */
+int alignn_b200_bn_finalize(const float* partials, int partial_rows, int partial_stride /*floats between rows*/,
+                            int which /*0: cols {0,1}; 1: cols {2,3} of the partial row*/,
+                            int64_t count, int d, const float* gamma, const float* beta, float eps, float momentum,
+                            float* running_mean, float* running_var /* may be NULL */,
+                            float* scale, float* shift, float* mean, float* rstd, alignn_stream_t stream);
+
+/* BatchNorm1d train mode, step 3: out = (residual ? res : 0) + silu(R*scale + shift), rows [n,d]. */
+int alignn_b200_affine_silu_residual(const float* R, const float* res, const float* scale, const float* shift,
+                                     float* out, int64_t n, int d, alignn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Backward of the same stage.  Produces
+ *   GM [Ne,d]  = dL/dm            (feeds  dL/dy += GM W_eg,  dL/dW_eg = GM^T y)
+ *   GP [Nn,4d] = dL/dP            (feeds  dL/dx += GP Wcat,  dL/dWcat = GP^T x,  bias grads = colsum)
+ *   norm parameter gradients as per-block partials.
+ * The residual part of dL/dx, dL/dy (identity) is added by the caller.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  size_t struct_size;
+  int64_t Nn, Ne;
+  int32_t d;
+  int32_t norm_nodes, norm_edges; /* LAYER, AFFINE (eval BN), STATS (train BN: needs bn_c1/bn_c2) */
+  float gate_eps, ln_eps;
+  /* saved from forward */
+  const float* P; const float* M; const float* XP; const float* S; const float* H;
+  const int32_t* src; const int32_t* dst;
+  const int32_t* in_ptr; const int32_t* in_eid;
+  const int32_t* out_ptr; const int32_t* out_eid;
+  /* norm params: LAYER (gamma,beta); AFFINE/STATS (scale,shift) plus, for both, mean/rstd [d]
+     (AFFINE/STATS only; used to form xhat for the gamma gradient) */
+  const float* n_w; const float* n_b; const float* n_mean; const float* n_rstd;
+  const float* e_w; const float* e_b; const float* e_mean; const float* e_rstd;
+  /* STATS only: c1 = sum(gu)/count, c2 = sum(gu*xhat)/count per channel (from bn_backward_reduce) */
+  const float* n_c1; const float* n_c2; const float* e_c1; const float* e_c2;
+  /* incoming gradients */
+  const float* gx_out;  /* [Nn,d] */
+  const float* gy_out;  /* [Ne,d] or NULL (edge output unused) */
+  /* outputs */
+  float* GM; float* GP;
+  float* GSh;           /* [Nn,d] workspace: dL/d(sum_sigma_h) */
+  /* per-block partials of the destination-keyed pass, [partial_rows, 6, d] =
+       {sum gu_e*xhat_e, sum gu_e, sum gu_n*xhat_n, sum gu_n, sum dL/dx', sum dL/d e_dst}
+     (column sums of rows 0..3 are the norm weight/bias gradients; rows 4,5 are the bias gradients
+      of src_update and of dst_gate == edge_gate == src_gate) */
+  float* partials;
+  /* per-block partials of the source-keyed pass, [partial_rows, 2, d] = {sum dL/d e_src, sum dL/d Bh} */
+  float* partials_src;
+  alignn_stream_t stream;
+} alignn_b200_egc_bwd_args;
+
+int alignn_b200_egc_backward(const alignn_b200_egc_bwd_args* args);
+
+/* BatchNorm train-mode backward, pass 1: per-block partials of sum(gu) and sum(gu*xhat) over rows,
+ * gu = g_out * silu'(R*scale+shift), xhat = (R-mean)*rstd.  partials: [rows_out, 2, d]. */
+int alignn_b200_bn_backward_reduce(const float* R, const float* g_out, const float* scale, const float* shift,
+                                   const float* mean, const float* rstd, int64_t n, int d,
+                                   float* partials, int partial_rows, alignn_stream_t stream);
+
+/* Deterministic column sum of a [rows, cols] fp32 matrix with row stride `stride` floats into
+ * out[cols] (fp64 accumulation), optionally scaled by `alpha`. */
+int alignn_b200_colsum(const float* a, int64_t rows, int cols, int64_t stride, float alpha, float* out,
+                       alignn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Gather / segment-sum primitive alone (BASELINE.json config 5; DGL update_all(u_mul_e,sum) +
+ * update_all(copy_e,sum), alignn.py:105-108):  Sh[v] = sum_{e->v} Bh[src e]*sigma[e],
+ * S[v] = sum_{e->v} sigma[e].
+ * ---------------------------------------------------------------------------------------- */
+int alignn_b200_gather_segment_sum(const float* Bh, const float* sigma, const int32_t* src,
+                                   const int32_t* in_ptr, const int32_t* in_eid, int64_t Nn, int64_t Ne, int d,
+                                   float* Sh, float* S, alignn_stream_t stream);
+
+/* Per-graph mean over node rows (dgl.nn.AvgPooling, alignn.py:325) and its backward. */
+int alignn_b200_segment_mean(const float* x, const int32_t* graph_ptr /*[B+1]*/, int64_t B, int d, float* out,
+                             alignn_stream_t stream);
+int alignn_b200_segment_mean_backward(const float* g_out /*[B,d]*/, const int32_t* graph_ptr, int64_t B, int d,
+                                      float* gx /*[N,d]*/, alignn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALIGNN_B200_H */

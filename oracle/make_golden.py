@@ -178,6 +178,8 @@ def main():
             orc = O.ALIGNN(norm="batchnorm", **cfg).to(dtype)
             orc.load_state_dict(ref.state_dict())
             for train in (True, False):
+                GI.fill_state_dict(ref, 300)          # fresh running statistics for each mode
+                orc.load_state_dict(ref.state_dict())
                 outs = []
                 for mod, conv in ((ref, to_dgl), (orc, to_oracle)):
                     mod.train(train)

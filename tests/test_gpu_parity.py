@@ -1,0 +1,243 @@
+"""GPU (-m gpu): the CUDA path, called through the product API / C ABI, against the CPU oracle and
+the golden vectors of the unmodified reference.  Tolerance: 1e-4 relative (BASELINE north_star),
+measured against each tensor's max magnitude; index arrays are compared bit-exactly in
+tests/test_host_logic.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from alignn_b200 import ops, synthetic
+from alignn_b200.alignn import ALIGNN, ALIGNNConfig, EdgeGatedGraphConv
+from alignn_b200.alignn_atomwise import EdgeGatedGraphConv as EdgeGatedGraphConvLN
+from alignn_b200.graph import Graph
+from oracle import alignn_oracle as O
+from oracle import golden_inputs as GI
+from tests.helpers import REL_TOL, assert_close, rel_err, to_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+CONV_TAGS = [("bn_train", "batchnorm", True), ("bn_eval", "batchnorm", False), ("ln", "layernorm", True)]
+
+
+def _make_conv(norm, d, seed, train):
+    conv = (EdgeGatedGraphConv if norm == "batchnorm" else EdgeGatedGraphConvLN)(d, d)
+    GI.fill_state_dict(conv, seed)
+    conv.train(train)
+    return conv.to(DEV)
+
+
+def _run_conv(conv, g, x, y, seed, d, need_edge_out=True):
+    wx = GI.features(seed + 1, x.shape[0], d).to(DEV)
+    wy = GI.features(seed + 2, y.shape[0], d).to(DEV)
+    xi = x.to(DEV).clone().requires_grad_(True)
+    yi = y.to(DEV).clone().requires_grad_(True)
+    xo, yo = conv(g.to(DEV), xi, yi, _need_edge_out=need_edge_out)
+    loss = (xo * wx).sum() + ((yo * wy).sum() if need_edge_out else 0.0)
+    params = [p for p in conv.parameters()]
+    grads = torch.autograd.grad(loss, [xi, yi] + params, allow_unused=True)
+    out = {"x_out": xo, "y_out": yo, "gx": grads[0], "gy": grads[1]}
+    for (n, p), gr in zip(conv.named_parameters(), grads[2:]):
+        out["g." + n] = torch.zeros_like(p) if gr is None else gr
+    if isinstance(conv.bn_nodes, torch.nn.BatchNorm1d):
+        for bn in ("bn_nodes", "bn_edges"):
+            out[f"{bn}.running_mean"] = getattr(conv, bn).running_mean
+            out[f"{bn}.running_var"] = getattr(conv, bn).running_var
+    return out
+
+
+def _oracle_conv(norm, train, og, x, y, d, seed, need_edge_out=True, dtype=torch.float64):
+    conv = O.EdgeGatedGraphConv(d, d, norm=norm).to(dtype)
+    GI.fill_state_dict(conv, seed)
+    conv.train(train)
+    wx = GI.features(seed + 1, x.shape[0], d).to(dtype)
+    wy = GI.features(seed + 2, y.shape[0], d).to(dtype)
+    xi = x.to(dtype).clone().requires_grad_(True)
+    yi = y.to(dtype).clone().requires_grad_(True)
+    xo, yo = conv(og, xi, yi)
+    loss = (xo * wx).sum() + ((yo * wy).sum() if need_edge_out else 0.0)
+    grads = torch.autograd.grad(loss, [xi, yi] + list(conv.parameters()), allow_unused=True)
+    out = {"x_out": xo, "y_out": yo, "gx": grads[0], "gy": grads[1]}
+    for (n, p), gr in zip(conv.named_parameters(), grads[2:]):
+        out["g." + n] = torch.zeros_like(p) if gr is None else gr
+    if norm == "batchnorm":
+        for bn in ("bn_nodes", "bn_edges"):
+            out[f"{bn}.running_mean"] = getattr(conv, bn).running_mean
+            out[f"{bn}.running_var"] = getattr(conv, bn).running_var
+    return out
+
+
+@pytest.mark.parametrize("tag,norm,train", CONV_TAGS)
+def test_conv_jvasp_vs_reference_golden(golden_dir, tag, norm, train):
+    """BASELINE config 1 (32 atoms, d=64) against the unmodified reference's outputs."""
+    gold = np.load(os.path.join(golden_dir, "conv_jvasp_d64.npz"))
+    jv = np.load(os.path.join(golden_dir, "jvasp_98225.npz"))
+    g = Graph(jv["src"], jv["dst"], 32)
+    x, y = GI.features(11, 32, 64), GI.features(12, g.num_edges(), 64)
+    out = _run_conv(_make_conv(norm, 64, 100, train), g, x, y, 100, 64)
+    for k, v in out.items():
+        assert_close(v, gold[f"{tag}.{k}"], what=f"{tag}.{k}")
+
+
+@pytest.mark.parametrize("tag,norm,train", CONV_TAGS)
+def test_conv_linegraph_d256_vs_reference_golden(golden_dir, tag, norm, train):
+    gold = np.load(os.path.join(golden_dir, "conv_lg_d256.npz"))
+    g, lg, _, _ = synthetic.make_batch(batch_size=1, atoms=10, k=12, seed=5)
+    xm, z = GI.features(21, g.num_edges(), 256), GI.features(22, lg.num_edges(), 256)
+    out = _run_conv(_make_conv(norm, 256, 200, train), lg, xm, z, 200, 256)
+    for k in ("x_out", "gx", "g.edge_gate.weight", "g.src_gate.bias", "g.bn_edges.weight", "g.bn_nodes.bias",
+              "g.dst_update.weight"):
+        assert_close(out[k], gold[f"{tag}.{k}"], what=f"{tag}.{k}")
+    assert_close(out["y_out"][::7], gold[f"{tag}.y_out_s"], what="y_out")
+    assert_close(out["gy"][::7], gold[f"{tag}.gy_s"], what="gy")
+
+
+@pytest.mark.parametrize("norm,train", [("batchnorm", True), ("layernorm", True), ("batchnorm", False)])
+@pytest.mark.parametrize("d", [32, 64, 128, 256])
+def test_conv_all_widths_ragged_graph(norm, train, d):
+    """Ragged k-NN multigraph (variable in-degree, multi-edges, self-image bonds), every supported d."""
+    g, _, _, _ = synthetic.make_batch(batch_size=3, atoms=9, k=8, seed=d, regular=False, vary_atoms=True)
+    x, y = GI.features(1, g.num_nodes(), d), GI.features(2, g.num_edges(), d)
+    out = _run_conv(_make_conv(norm, d, 7, train), g, x, y, 7, d)
+    ref = _oracle_conv(norm, train, to_oracle(g), x, y, d, 7)
+    for k in ref:
+        assert_close(out[k], ref[k], what=f"{norm} d={d} {k}")
+
+
+def test_conv_dead_edge_output():
+    """_need_edge_out=False (last ALIGNN layer's z, last GCN layer's y)."""
+    g, lg, _, _ = synthetic.make_batch(batch_size=2, atoms=6, k=6, seed=8)
+    d = 64
+    x, y = GI.features(1, lg.num_nodes(), d), GI.features(2, lg.num_edges(), d)
+    for norm, train in (("batchnorm", True), ("layernorm", True)):
+        out = _run_conv(_make_conv(norm, d, 9, train), lg, x, y, 9, d, need_edge_out=False)
+        ref = _oracle_conv(norm, train, to_oracle(lg), x, y, d, 9, need_edge_out=False)
+        assert out["y_out"] is None
+        for k in ref:
+            if k == "y_out":
+                continue
+            assert_close(out[k], ref[k], what=f"dead {norm} {k}")
+
+
+def test_conv_edge_cases_isolated_nodes_and_hubs():
+    """In-degree 0 nodes (sum over no edges = 0, alignn.py:105-109) and a hub with 70 in-edges
+    (more than one 32-edge chunk per warp)."""
+    rng = np.random.default_rng(0)
+    n = 12
+    src = np.concatenate([rng.integers(0, n, 70), rng.integers(0, n, 20)])
+    dst = np.concatenate([np.full(70, 3), rng.integers(4, 8, 20)])      # nodes 0-2, 8-11 have no in-edges
+    g = Graph(src, dst, n)
+    d = 64
+    x, y = GI.features(3, n, d), GI.features(4, g.num_edges(), d)
+    for norm in ("batchnorm", "layernorm"):
+        out = _run_conv(_make_conv(norm, d, 5, True), g, x, y, 5, d)
+        ref = _oracle_conv(norm, True, to_oracle(g), x, y, d, 5)
+        for k in ref:
+            assert_close(out[k], ref[k], what=f"edge-case {norm} {k}")
+
+
+def test_gather_segment_sum_primitive():
+    """BASELINE config 5 primitive at 1e5 edges vs index_add; plus linearity at full size."""
+    g, bh, sigma = synthetic.make_segment_sweep(100_000, d=256)
+    gd = g.to(DEV)
+    Sh, S = ops.gather_segment_sum(gd.index, bh.to(DEV), sigma.to(DEV))
+    s, d = g.edges()
+    ref_Sh = torch.zeros_like(bh, dtype=torch.float64).index_add(0, d.long(), (bh[s.long()] * sigma).double())
+    ref_S = torch.zeros_like(bh, dtype=torch.float64).index_add(0, d.long(), sigma.double())
+    assert_close(Sh, ref_Sh, tol=1e-5, what="Sh")
+    assert_close(S, ref_S, tol=1e-5, what="S")
+    # size-independent property: Sh is linear in Bh, S does not depend on Bh
+    Sh2, S2 = ops.gather_segment_sum(gd.index, 2 * bh.to(DEV), sigma.to(DEV))
+    assert torch.equal(Sh2, 2 * Sh) and torch.equal(S2, S)
+
+
+SMALL_CFG = dict(alignn_layers=2, gcn_layers=2, hidden_features=64, embedding_features=32)
+GRAD_KEYS = ("fc.weight", "atom_embedding.layer.0.weight", "alignn_layers.0.edge_update.edge_gate.weight",
+             "alignn_layers.1.node_update.src_gate.weight", "gcn_layers.1.dst_update.bias",
+             "alignn_layers.0.node_update.bn_nodes.weight", "gcn_layers.0.bn_edges.bias",
+             "angle_embedding.1.layer.0.weight")
+
+
+@pytest.mark.parametrize("case", ["reg", "knn"])
+@pytest.mark.parametrize("train", [True, False])
+def test_full_alignn_vs_reference_golden(golden_dir, case, train):
+    gold = np.load(os.path.join(golden_dir, "alignn_small.npz"))
+    if case == "reg":
+        g, lg, lat, tgt = synthetic.make_batch(batch_size=3, atoms=9, k=12, seed=31, vary_atoms=True)
+    else:
+        g, lg, lat, tgt = synthetic.make_batch(batch_size=2, atoms=6, k=6, seed=32, regular=False)
+    m = ALIGNN(ALIGNNConfig(name="alignn", **SMALL_CFG))
+    GI.fill_state_dict(m, 300)
+    m.to(DEV).train(train)
+    out = m((g.to(DEV), lg.to(DEV), lat.to(DEV)))
+    loss = (out - tgt.to(DEV)).abs().mean()
+    loss.backward()
+    tag = f"{case}.{'train' if train else 'eval'}"
+    assert_close(out, gold[tag + ".out"], what="out")
+    grads = dict(m.named_parameters())
+    for k in GRAD_KEYS:
+        gr = grads[k].grad
+        got = torch.zeros_like(grads[k]) if gr is None else gr
+        ref = gold[f"{tag}.g.{k}"]
+        if np.abs(ref).max() == 0:
+            assert float(got.abs().max()) == 0.0, k       # unused parameters (App. D-11) get no gradient
+        else:
+            assert_close(got, ref, tol=2e-4, what=k)
+
+
+def test_full_size_batch64_vs_oracle():
+    """BASELINE configs 2/3 at full size (B=64, n=30, k=12, 4+4 layers, d=256): inference output and
+    training loss + a gradient against the fp32 CPU oracle (the fp64 oracle needs minutes)."""
+    g, lg, lat, tgt = synthetic.make_batch(batch_size=64, atoms=30, k=12, seed=123)
+    m = ALIGNN(ALIGNNConfig(name="alignn"))
+    GI.fill_state_dict(m, 1234)
+    orc = O.ALIGNN()
+    orc.load_state_dict(m.state_dict())
+    m.to(DEV)
+    gd, lgd, latd = g.to(DEV), lg.to(DEV), lat.to(DEV)
+    m.eval()
+    orc.eval()
+    with torch.no_grad():
+        out = m((gd, lgd, latd))
+        ref = orc((to_oracle(g), to_oracle(lg), lat))
+    assert_close(out, ref, what="batch-64 inference")
+    m.train()
+    orc.train()
+    out = m((gd, lgd, latd))
+    (out - tgt.to(DEV)).abs().mean().backward()
+    ref = orc((to_oracle(g), to_oracle(lg), lat))
+    (ref - tgt).abs().mean().backward()
+    assert_close(out, ref, what="batch-64 train forward")
+    for name in ("alignn_layers.0.edge_update.edge_gate.weight", "gcn_layers.3.src_update.weight", "fc.weight",
+                 "alignn_layers.3.node_update.bn_nodes.weight"):
+        a = dict(m.named_parameters())[name].grad
+        b = dict(orc.named_parameters())[name].grad
+        assert_close(a, b, tol=5e-4, what=name)   # fp32 oracle itself carries ~1e-5 of summation noise
+
+
+def test_deterministic_and_graph_not_mutated():
+    g, lg, lat, tgt = synthetic.make_batch(batch_size=4, atoms=10, k=12, seed=77)
+    m = ALIGNN(ALIGNNConfig(name="alignn", **SMALL_CFG)).to(DEV).train()
+    gd, lgd = g.to(DEV), lg.to(DEV)
+    keys = (set(gd.ndata), set(gd.edata), set(lgd.ndata), set(lgd.edata))
+    outs, grads = [], []
+    for _ in range(2):
+        m.zero_grad()
+        out = m((gd, lgd, lat.to(DEV)))
+        out.sum().backward()
+        outs.append(out.detach().clone())
+        grads.append(m.alignn_layers[0].edge_update.edge_gate.weight.grad.clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(grads[0], grads[1])       # no float atomics anywhere
+    assert keys == (set(gd.ndata), set(gd.edata), set(lgd.ndata), set(lgd.edata))   # inputs are borrowed
+
+
+def test_launch_counter_counts_library_kernels():
+    from alignn_b200 import _lib
+    g, _, _, _ = synthetic.make_batch(batch_size=1, atoms=6, k=6, seed=2)
+    conv = _make_conv("layernorm", 64, 3, True)
+    before = _lib.launch_count()
+    with torch.no_grad():
+        conv(g.to(DEV), GI.features(1, g.num_nodes(), 64).to(DEV), GI.features(2, g.num_edges(), 64).to(DEV))
+    assert _lib.launch_count() - before == 1      # one fused kernel per conv in inference

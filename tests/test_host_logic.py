@@ -1,0 +1,177 @@
+"""CPU: host logic (graph container, sorted-CSR index, line graph, collation), the C-ABI library
+loads and exports every symbol the header declares, ctypes struct layouts match the C structs,
+and the product path refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import alignn_b200
+from alignn_b200 import _lib, synthetic
+from alignn_b200.graph import EdgeIndex, Graph, batch, reverse, unbatch
+from oracle import alignn_oracle as O
+from tests.helpers import to_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    ge.build()
+
+
+@pytest.mark.parametrize("seed,regular", [(1, True), (2, False), (3, False)])
+def test_edge_index_bit_exact(seed, regular):
+    g, lg, _, _ = synthetic.make_batch(batch_size=3, atoms=7, k=6, seed=seed, regular=regular, vary_atoms=True)
+    for gr in (g, lg):
+        s, d = gr.edges()
+        ip, ie = O.csr_by_key(d.numpy(), gr.num_nodes())
+        op, oe = O.csr_by_key(s.numpy(), gr.num_nodes())
+        ix = gr.index
+        assert ix.in_ptr.dtype == torch.int32
+        assert np.array_equal(ix.in_ptr.numpy(), ip) and np.array_equal(ix.in_eid.numpy(), ie)
+        assert np.array_equal(ix.out_ptr.numpy(), op) and np.array_equal(ix.out_eid.numpy(), oe)
+    assert lg.index.dst_sorted and np.array_equal(lg.index.in_eid.numpy(), np.arange(lg.num_edges()))
+
+
+def test_line_graph_same_edge_set_as_reference_semantics():
+    g, lg, _, _ = synthetic.make_batch(batch_size=2, atoms=5, k=6, seed=11, regular=False)
+    og = to_oracle(g)
+    olg = O.line_graph(og)           # DGL order (i, j)
+    ours = set(zip(lg.edges()[0].tolist(), lg.edges()[1].tolist()))
+    # multigraph: compare as multisets
+    a = sorted(zip(lg.edges()[0].tolist(), lg.edges()[1].tolist()))
+    b = sorted(zip(olg.src.tolist(), olg.dst.tolist()))
+    assert a == b and len(ours) > 0
+    assert lg.num_nodes() == g.num_edges()
+    assert lg.batch_num_edges().tolist() == olg.bne.tolist()
+    # within each destination, sources ascend (same summation order as the reference)
+    s, d = lg.edges()
+    for v in range(0, lg.num_nodes(), 7):
+        seg = s[d == v].tolist()
+        assert seg == sorted(seg)
+    # cosines: same values edge-for-edge after aligning the two orders
+    h_ours = alignn_b200.bond_cosines(g.edata["r"], lg)
+    h_ref = O.bond_cosines(og.edata["r"], olg.src, olg.dst)
+    key = lambda s_, d_: np.lexsort((s_, d_))  # noqa: E731
+    np.testing.assert_array_equal(h_ours.numpy()[key(s.numpy(), d.numpy())],
+                                  h_ref.numpy()[key(olg.src.numpy(), olg.dst.numpy())])
+
+
+def test_line_graph_self_loops_and_multi_edges():
+    # node 0 has a self loop (edge 0) and a double bond to node 1 (edges 1, 2), reverse edges 3, 4
+    g = Graph([0, 0, 0, 1, 1], [0, 1, 1, 0, 0], 2)
+    lg = g.line_graph(shared=True)
+    pairs = sorted(zip(lg.edges()[0].tolist(), lg.edges()[1].tolist()))
+    expect = sorted((i, j) for i in range(5) for j in range(5)
+                    if i != j and [0, 1, 1, 0, 0][i] == [0, 0, 0, 1, 1][j])
+    assert pairs == expect
+    assert (0, 0) not in pairs        # a bond never pairs with itself, even when it is a self loop
+
+
+def test_headline_shapes():
+    g, lg, lat, y = synthetic.make_batch(batch_size=64, atoms=30, k=12, seed=123)
+    assert (g.num_nodes(), g.num_edges(), lg.num_edges()) == (1920, 23040, 276480)
+    assert lat.shape == (64, 3, 3) and y.shape == (64,)
+    s, d = g.edges()
+    assert torch.equal(s[0::2], d[1::2]) and torch.equal(d[0::2], s[1::2])          # reverse bonds adjacent
+    assert torch.equal(g.edata["r"][0::2], -g.edata["r"][1::2])
+    assert float(torch.norm(g.edata["r"], dim=1).min()) >= 1.5
+
+
+def test_batch_unbatch_reverse_roundtrip():
+    rng = np.random.default_rng(0)
+    gs = [synthetic.make_crystal(rng, n, 6, False)[0] for n in (3, 5, 4)]
+    bg = batch(gs)
+    assert bg.batch_size == 3 and bg.batch_num_nodes().tolist() == [3, 5, 4]
+    back = unbatch(bg)
+    for a, b in zip(gs, back):
+        assert torch.equal(a.edges()[0], b.edges()[0]) and torch.equal(a.edges()[1], b.edges()[1])
+        assert torch.equal(a.edata["r"], b.edata["r"])
+    rg = reverse(bg, copy_edata=True)
+    assert torch.equal(rg.edges()[0], bg.edges()[1]) and torch.equal(rg.index.in_ptr, bg.index.out_ptr)
+    assert bg.local_var().ndata is not bg.ndata
+    assert bg.node_graph_offsets().tolist() == [0, 3, 8, 12]
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "alignn_b200.h")).read()
+    declared = set(re.findall(r"\b(alignn_b200_[a-z_0-9]+)\s*\(", header))
+    declared -= {"alignn_b200_status", "alignn_b200_norm"}
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.alignn_b200_version() == 100
+    assert lib.alignn_b200_strerror(-2).decode().startswith("unsupported feature width")
+    assert lib.alignn_b200_egc_partial_rows(1920, 256) == 240
+    assert lib.alignn_b200_egc_partial_rows(10 ** 7, 256) == 148 * 4
+
+
+def test_ctypes_structs_match_c_layout(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "alignn_b200.h"\n'
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(alignn_b200_egc_fwd_args),'
+                   'offsetof(alignn_b200_egc_fwd_args, x), offsetof(alignn_b200_egc_fwd_args, stream),'
+                   'sizeof(alignn_b200_egc_bwd_args), offsetof(alignn_b200_egc_bwd_args, P),'
+                   'offsetof(alignn_b200_egc_bwd_args, stream));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(t) for t in subprocess.check_output([str(exe)]).split()]
+    F, B = _lib.EgcFwdArgs, _lib.EgcBwdArgs
+    assert got == [ctypes.sizeof(F), F.x.offset, F.stream.offset, ctypes.sizeof(B), B.P.offset, B.stream.offset]
+
+
+def test_bad_arguments_are_rejected_without_touching_the_gpu():
+    lib = _lib.load()
+    a = _lib.EgcFwdArgs(struct_size=1)
+    assert lib.alignn_b200_egc_forward(ctypes.byref(a)) == -3
+    a = _lib.EgcFwdArgs(struct_size=ctypes.sizeof(_lib.EgcFwdArgs), d=48, Nn=4, Ne=4)
+    assert lib.alignn_b200_egc_forward(ctypes.byref(a)) == -2
+    a = _lib.EgcFwdArgs(struct_size=ctypes.sizeof(_lib.EgcFwdArgs), d=64, Nn=4, Ne=4)
+    assert lib.alignn_b200_egc_forward(ctypes.byref(a)) == -1          # NULL pointers
+    assert lib.alignn_b200_colsum(None, 1, 1, 1, 1.0, None, None) == -1
+
+
+def test_no_cpu_fallback():
+    from alignn_b200.alignn import ALIGNN, ALIGNNConfig, EdgeGatedGraphConv
+    g, lg, lat, _ = synthetic.make_batch(batch_size=1, atoms=4, k=4, seed=1)
+    conv = EdgeGatedGraphConv(64, 64)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        conv(g, torch.zeros(g.num_nodes(), 64), torch.zeros(g.num_edges(), 64))
+    with pytest.raises(RuntimeError, match="fp32-only"):
+        conv(g, torch.zeros(g.num_nodes(), 64, dtype=torch.float64), torch.zeros(g.num_edges(), 64, dtype=torch.float64))
+    with pytest.raises(NotImplementedError):
+        EdgeGatedGraphConv(32, 64)
+    m = ALIGNN(ALIGNNConfig(name="alignn", alignn_layers=1, gcn_layers=1, hidden_features=32, embedding_features=32))
+    with pytest.raises(RuntimeError):
+        m((g, lg, lat))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "alignn_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            txt = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in txt and "from oracle" not in txt, fn
+
+
+def test_state_dict_names_match_reference_layout():
+    from alignn_b200.alignn import ALIGNN, ALIGNNConfig
+    m = ALIGNN(ALIGNNConfig(name="alignn"))
+    o = O.ALIGNN()
+    assert list(m.state_dict().keys()) == list(o.state_dict().keys())
+    assert sum(p.numel() for p in m.parameters()) == 4026753
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(o.state_dict()[k].shape), k
+    cfg = ALIGNNConfig(name="alignn")
+    assert (cfg.alignn_layers, cfg.gcn_layers, cfg.hidden_features, cfg.atom_input_features) == (4, 4, 256, 92)
+    with pytest.raises(Exception):
+        ALIGNNConfig(name="not_alignn")
