@@ -15,6 +15,30 @@ from ._lib import NORM_AFFINE, NORM_LAYER, NORM_STATS, ptr, require_cuda, stream
 from .graph import EdgeIndex
 
 
+class KernelTimer:
+    """Optional CUDA-event timing of individual library calls (used by bench.py for the roofline
+    of the dominant kernel: events are recorded on the launching stream, inside the timed region)."""
+
+    def __init__(self, min_edges: int = 0):
+        self.min_edges = min_edges
+        self.records = {}      # name -> list of (start_event, end_event, algorithmic_bytes)
+
+    def span(self, name: str, nbytes: int):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.records.setdefault(name, []).append((s, e, nbytes))
+        return s, e
+
+    def summary(self):
+        out = {}
+        for name, rec in self.records.items():
+            ms = [s.elapsed_time(e) for s, e, _ in rec]
+            out[name] = dict(launches=len(ms), avg_ms=sum(ms) / len(ms), bytes=rec[0][2])
+        return out
+
+
+TIMER: Optional[KernelTimer] = None
+
+
 def _check_d(d: int) -> None:
     if d not in _lib.SUPPORTED_D:
         raise RuntimeError(f"alignn_b200: unsupported feature width {d}; supported: {_lib.SUPPORTED_D}")
@@ -51,7 +75,17 @@ def egc_forward(ix: EdgeIndex, x, y, G, P, n_w, n_b, e_w, e_b, *, norm_nodes: in
         n_w=ptr(n_w), n_b=ptr(n_b), e_w=ptr(e_w), e_b=ptr(e_b),
         x_out=ptr(x_out), y_out=ptr(y_out), M=ptr(M), XP=ptr(XP), S=ptr(S), H=ptr(H), partials=ptr(partials),
         stream=stream_ptr())
+    span = None
+    if TIMER is not None and Ne >= TIMER.min_edges:
+        # compulsory bytes of THIS kernel: read G, P (each element once), indices; write what it writes
+        nb = 4 * d * (Ne + 4 * Nn) + 4 * Ne + 4 * (Nn + 1)
+        nb += 4 * d * Ne * (M is not None) + 4 * d * Nn * 3 * (XP is not None)
+        nb += 4 * d * Ne * (1 + int(residual)) * (y_out is not None) + 4 * d * Nn * (1 + int(residual)) * (x_out is not None)
+        span = TIMER.span("egc_forward_kernel", nb)
+        span[0].record()
     _lib.check(lib.alignn_b200_egc_forward(C.byref(a)), "alignn_b200_egc_forward")
+    if span is not None:
+        span[1].record()
     return dict(x_out=x_out, y_out=y_out, M=M, XP=XP, S=S, H=H, partials=partials)
 
 

@@ -28,6 +28,28 @@ def rel_err(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
 
 
-def assert_close(a, b, tol=REL_TOL, what=""):
-    e = rel_err(a, b)
-    assert e <= tol, f"{what}: rel err {e:.3e} > {tol:.1e}"
+def assert_close(a, b, tol=REL_TOL, what="", atol=2e-6, floor=0.0):
+    """max|a-b| <= tol * max(max|b|, floor) + atol.  `floor` / `atol` only matter for tensors that are
+    mathematically zero in the reference (e.g. the gradient of a bias that feeds a train-mode
+    BatchNorm): there the error is judged against the scale of the sibling gradients."""
+    a = torch.as_tensor(np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a), dtype=torch.float64)
+    b = torch.as_tensor(np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b), dtype=torch.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if a.numel() == 0:
+        return
+    err = (a - b).abs().max().item()
+    scale = b.abs().max().item()
+    assert err <= tol * max(scale, floor) + atol, f"{what}: max abs err {err:.3e} vs scale {scale:.3e} (rel {err / max(scale, 1e-30):.3e} > {tol:.1e})"
+
+
+def assert_dict_close(out, ref, tol=REL_TOL, what="", keys=None):
+    """Compare every tensor of `ref`; parameter gradients ('g.*') that are ~0 in the reference are
+    judged against 1% of the largest parameter-gradient magnitude of the same layer."""
+    def mx(v):
+        v = v.detach().cpu() if isinstance(v, torch.Tensor) else torch.as_tensor(np.asarray(v))
+        return float(v.abs().max()) if v.numel() else 0.0
+    gfloor = 1e-2 * max([mx(v) for k, v in ref.items() if k.startswith("g.")] or [0.0])
+    for k in (keys or ref.keys()):
+        if out[k] is None and ref[k] is None:
+            continue
+        assert_close(out[k], ref[k], tol=tol, what=f"{what} {k}", floor=gfloor if k.startswith("g.") else 0.0)

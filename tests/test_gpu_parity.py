@@ -14,7 +14,7 @@ from alignn_b200.alignn_atomwise import EdgeGatedGraphConv as EdgeGatedGraphConv
 from alignn_b200.graph import Graph
 from oracle import alignn_oracle as O
 from oracle import golden_inputs as GI
-from tests.helpers import REL_TOL, assert_close, rel_err, to_oracle
+from tests.helpers import REL_TOL, assert_close, assert_dict_close, rel_err, to_oracle
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -77,8 +77,8 @@ def test_conv_jvasp_vs_reference_golden(golden_dir, tag, norm, train):
     g = Graph(jv["src"], jv["dst"], 32)
     x, y = GI.features(11, 32, 64), GI.features(12, g.num_edges(), 64)
     out = _run_conv(_make_conv(norm, 64, 100, train), g, x, y, 100, 64)
-    for k, v in out.items():
-        assert_close(v, gold[f"{tag}.{k}"], what=f"{tag}.{k}")
+    ref = {k: gold[f"{tag}.{k}"] for k in out}
+    assert_dict_close(out, ref, what=tag)
 
 
 @pytest.mark.parametrize("tag,norm,train", CONV_TAGS)
@@ -102,8 +102,7 @@ def test_conv_all_widths_ragged_graph(norm, train, d):
     x, y = GI.features(1, g.num_nodes(), d), GI.features(2, g.num_edges(), d)
     out = _run_conv(_make_conv(norm, d, 7, train), g, x, y, 7, d)
     ref = _oracle_conv(norm, train, to_oracle(g), x, y, d, 7)
-    for k in ref:
-        assert_close(out[k], ref[k], what=f"{norm} d={d} {k}")
+    assert_dict_close(out, ref, what=f"{norm} d={d}")
 
 
 def test_conv_dead_edge_output():
@@ -115,10 +114,7 @@ def test_conv_dead_edge_output():
         out = _run_conv(_make_conv(norm, d, 9, train), lg, x, y, 9, d, need_edge_out=False)
         ref = _oracle_conv(norm, train, to_oracle(lg), x, y, d, 9, need_edge_out=False)
         assert out["y_out"] is None
-        for k in ref:
-            if k == "y_out":
-                continue
-            assert_close(out[k], ref[k], what=f"dead {norm} {k}")
+        assert_dict_close(out, ref, what=f"dead {norm}", keys=[k for k in ref if k != "y_out"])
 
 
 def test_conv_edge_cases_isolated_nodes_and_hubs():
@@ -134,8 +130,7 @@ def test_conv_edge_cases_isolated_nodes_and_hubs():
     for norm in ("batchnorm", "layernorm"):
         out = _run_conv(_make_conv(norm, d, 5, True), g, x, y, 5, d)
         ref = _oracle_conv(norm, True, to_oracle(g), x, y, d, 5)
-        for k in ref:
-            assert_close(out[k], ref[k], what=f"edge-case {norm} {k}")
+        assert_dict_close(out, ref, what=f"edge-case {norm}")
 
 
 def test_gather_segment_sum_primitive():
