@@ -60,10 +60,11 @@ class _EdgeGatedConvFn(torch.autograd.Function):
         Ne = y.shape[0]
         needs_grad = any(ctx.needs_input_grad)
         # node projections P = [e_src | Bh | e_dst | src_update] (include/alignn_b200.h) and edge gate G
+        # (tcgen05 bf16x3 GEMMs, csrc/gemm_tc.cu; weights are re-split every call because they change every step)
         Wcat = torch.cat([W_sg, W_du, W_dg, W_su], 0)
         bcat = torch.cat([b_sg, b_du, b_dg, b_su], 0)
-        P = torch.addmm(bcat, x, Wcat.t())
-        G = torch.addmm(b_eg, y, W_eg.t())
+        P = ops.gemm_nt(x, ops.WeightImage(Wcat), bcat)
+        G = ops.gemm_nt(y, ops.WeightImage(W_eg.contiguous()), b_eg.contiguous())
 
         n_aux = e_aux = None
         if cfg.norm_nodes == NORM_AFFINE:
@@ -132,18 +133,17 @@ class _EdgeGatedConvFn(torch.autograd.Function):
         GM, GP, vd, vs = ops.egc_backward(cfg.index, P, M, XP, S, H, gx_out, gy_out, n, e,
                                           norm_nodes=cfg.norm_nodes, norm_edges=cfg.norm_edges,
                                           gate_eps=GATE_EPS, ln_eps=cfg.ln_eps)
-        # GEMM halves of the backward (plain library GEMMs, fp32)
+        # GEMM halves of the backward on the tensor cores: data gradients (gemm_tc.cu, transposed weight
+        # images, residual added in the epilogue) and weight gradients (wgrad_tc.cu, split-K over rows)
         need = ctx.needs_input_grad
         gx = gy = None
         if need[1]:
-            gx = torch.addmm(gx_out, GP, Wcat) if cfg.residual else GP @ Wcat
+            gx = ops.gemm_nt(GP, ops.WeightImage(Wcat, transpose=True), None, gx_out if cfg.residual else None)
         if need[2]:
-            if gy_out is not None and cfg.residual:
-                gy = torch.addmm(gy_out, GM, W_eg)
-            else:
-                gy = GM @ W_eg
-        gWcat = GP.t() @ x                      # [4d, d] rows: src_gate | dst_update | dst_gate | src_update
-        gW_eg = GM.t() @ y
+            gy = ops.gemm_nt(GM, ops.WeightImage(W_eg.contiguous(), transpose=True), None,
+                             gy_out if (gy_out is not None and cfg.residual) else None)
+        gWcat = ops.wgrad(GP, x, groups=4)      # [4d, d] rows: src_gate | dst_update | dst_gate | src_update
+        gW_eg = ops.wgrad(GM, y, groups=1)
         gW_sg, gW_du, gW_dg, gW_su = gWcat[0:d], gWcat[d:2 * d], gWcat[2 * d:3 * d], gWcat[3 * d:4 * d]
         gb_sg, gb_du = vs[0], vs[1]
         gb_su, gb_dg = vd[4], vd[5]

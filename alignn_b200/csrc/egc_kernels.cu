@@ -316,19 +316,28 @@ egc_backward_src_kernel(alignn_b200_egc_bwd_args a, float* __restrict__ partials
 // =============================================================================================
 // BatchNorm train-mode helpers
 // =============================================================================================
-// one block of d threads; fp64 accumulation over the per-block partial rows
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, int rows, int stride, int which, double count,
-                                   int d, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                   float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                                   float* mean_out, float* rstd_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= d) return;
+// 32 channels per block x 8 row lanes; fp64 accumulation over the per-block partial rows, fixed order
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ partials, int rows, int stride, int which, double count,
+                   int d, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                   float* mean_out, float* rstd_out) {
+  __shared__ double ss[8][32], sq[8][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double s = 0.0, q = 0.0;
-  const float* p = partials + (size_t)which * 2 * d + c;
-  for (int r = 0; r < rows; ++r) {
-    s += (double)p[(size_t)r * stride];
-    q += (double)p[(size_t)r * stride + d];
+  if (c < d) {
+    const float* p = partials + (size_t)which * 2 * d + c;
+    for (int r = rl; r < rows; r += 8) {
+      s += (double)p[(size_t)r * stride];
+      q += (double)p[(size_t)r * stride + d];
+    }
   }
+  ss[rl][cl] = s; sq[rl][cl] = q;
+  __syncthreads();
+  if (rl != 0 || c >= d) return;
+#pragma unroll
+  for (int k = 1; k < 8; ++k) { s += ss[k][cl]; q += sq[k][cl]; }
   const double mean = s / count;
   double var = q / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -398,14 +407,22 @@ bn_backward_reduce_kernel(const float* __restrict__ R, const float* __restrict__
   block_reduce_to_partials<D, 2>(acc, partials + (int64_t)blockIdx.x * 2 * D, red);
 }
 
-// out[c] = alpha * sum_r a[r*stride + c]; one thread per column, rows summed in fp64 in a fixed order.
-// Used on per-block partial buffers (rows <= kMaxBlocks), so the serial row loop is short.
-__global__ void colsum_kernel(const float* __restrict__ a, int64_t rows, int cols, int64_t stride, float alpha,
-                              float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+// out[c] = alpha * sum_r a[r*stride + c]; 32 columns per block x 8 row lanes, fp64, fixed order.
+// Used on per-block partial buffers (rows <= kMaxBlocks).
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ a, int64_t rows, int cols, int64_t stride, float alpha,
+              float* __restrict__ out) {
+  __shared__ double ss[8][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double s = 0.0;
-  for (int64_t r = 0; r < rows; ++r) s += (double)a[r * stride + c];
+  if (c < cols)
+    for (int64_t r = rl; r < rows; r += 8) s += (double)a[r * stride + c];
+  ss[rl][cl] = s;
+  __syncthreads();
+  if (rl != 0 || c >= cols) return;
+#pragma unroll
+  for (int k = 1; k < 8; ++k) s += ss[k][cl];
   out[c] = alpha * (float)s;
 }
 
@@ -494,16 +511,22 @@ __global__ void segment_mean_backward_kernel(const float* __restrict__ g_out, co
 // =============================================================================================
 #include <atomic>
 
-namespace {
+namespace alignn {
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_last_cuda_error{0};
-
-inline int check_launch() {
+int check_launch() {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_cuda_error.store((int)e); return ALIGNN_ERR_CUDA; }
   return ALIGNN_OK;
 }
+int record_cuda_error(int e) { g_last_cuda_error.store(e); return ALIGNN_ERR_CUDA; }
+}  // namespace alignn
+
+namespace {
+using alignn::check_launch;
+using alignn::g_launches;
+using alignn::g_last_cuda_error;
 inline bool supported_d(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
 inline int grid_for_rows(int64_t n) {
   int64_t b = (n + alignn::kWarpsPerBlock - 1) / alignn::kWarpsPerBlock;
@@ -571,7 +594,7 @@ int alignn_b200_bn_finalize(const float* partials, int partial_rows, int partial
   if (!partials || !scale || !shift || !mean || !rstd || partial_rows <= 0 || d <= 0 || count <= 0 ||
       (which != 0 && which != 1) || ((running_mean == nullptr) != (running_var == nullptr)))
     return ALIGNN_ERR_BAD_ARG;
-  alignn::bn_finalize_kernel<<<(d + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+  alignn::bn_finalize_kernel<<<(d + 31) / 32, 256, 0, (cudaStream_t)stream>>>(
       partials, partial_rows, partial_stride, which, (double)count, d, gamma, beta, eps, momentum, running_mean,
       running_var, scale, shift, mean, rstd);
   return check_launch();
@@ -629,7 +652,7 @@ int alignn_b200_bn_backward_reduce(const float* R, const float* g_out, const flo
 int alignn_b200_colsum(const float* a, int64_t rows, int cols, int64_t stride, float alpha, float* out,
                        alignn_stream_t stream) {
   if (!a || !out || rows < 0 || cols <= 0 || stride < cols) return ALIGNN_ERR_BAD_ARG;
-  alignn::colsum_kernel<<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a, rows, cols, stride, alpha, out);
+  alignn::colsum_kernel<<<(cols + 31) / 32, 256, 0, (cudaStream_t)stream>>>(a, rows, cols, stride, alpha, out);
   return check_launch();
 }
 

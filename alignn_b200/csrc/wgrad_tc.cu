@@ -1,0 +1,252 @@
+// Weight gradients of the Linear layers: C[g][o][i] = sum_r A[r, g*D + o] * B[r, i], r over the rows
+// (edges or nodes) of the batch -- a D x D output with a very long reduction (K = 276 480 rows for the
+// edge gate on L(g)).  Tensor cores via tcgen05.mma kind::f16, bf16x3 split (tc_common.cuh).
+//
+// Both operands are "MN-major" for this product (the contraction index is the ROW of the row-major
+// activations), so the loader threads convert fp32 -> bf16 hi/lo and store the canonical MN-major
+// SWIZZLE_NONE UMMA layout:  addr(mn, k) = (mn/8)*SBO + (k/8)*LBO + (k%8)*16 + (mn%8)*2,
+// SBO = 128 (next 8 channels), LBO = (rows_of_plane/8)*128 (next 8 rows of the contraction).
+//
+// Split-K: CTA c of group g reduces a contiguous slab of rows into a full D x D accumulator held in
+// TMEM (2 x 256 columns for D = 256), then writes its partial tile; a second kernel sums the partials
+// in a fixed order (deterministic, no float atomics).  Each input element is read from HBM exactly
+// once, which is the bound: the kernel moves 2*K*D*4 bytes.
+#include "tc_common.cuh"
+#include "api_common.h"
+#include "alignn_b200.h"
+
+namespace alignn {
+namespace wgrad {
+
+constexpr int BK = 32;          // contraction rows per stage (2 UMMA K=16 steps)
+constexpr int STAGES = 3;
+constexpr int LOAD_WARPS = 8;
+constexpr int LOADERS = LOAD_WARPS * 32;
+constexpr int THREADS = LOADERS + 32;
+constexpr uint32_t SBO = 128;
+constexpr int kNumSMsWgrad = 148;
+
+template <int D>
+struct Cfg {
+  static constexpr int MT = (D + 127) / 128;          // number of M=128 UMMA tiles
+  static constexpr int A_ROWS = MT * 128;             // padded channel count of the A plane
+  static constexpr int A_PLANE = A_ROWS * BK * 2;
+  static constexpr int B_PLANE = D * BK * 2;
+  static constexpr uint32_t LBO_A = (A_ROWS / 8) * 128;
+  static constexpr uint32_t LBO_B = (D / 8) * 128;
+  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
+  static constexpr int PIPE = STAGES * STAGE;
+  static constexpr int SMEM = PIPE + 128;
+  static constexpr int TMEM_COLS = (MT * D) < 32 ? 32 : (MT * D);     // 32, 64, 128, 512
+  static constexpr int TASKS = 2 * 4 * (D / 16);      // (matrix, 8-row group, 16-channel group) per stage
+};
+
+template <int D>
+__global__ void __launch_bounds__(THREADS, 1)
+wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int64_t K,
+                    int rows_per_cta, float* __restrict__ partials) {
+  using F = Cfg<D>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + F::PIPE);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accbar = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accbar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x, group = blockIdx.y;
+  const int64_t r_begin = (int64_t)cta * rows_per_cta;
+  const int64_t r_end = (r_begin + rows_per_cta < K) ? r_begin + rows_per_cta : K;
+  const int nk = r_end > r_begin ? (int)((r_end - r_begin + BK - 1) / BK) : 0;
+  const float* Ag = A + (int64_t)group * D;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], LOADERS); tc::mbar_init(&empty[s], 1); }
+    tc::mbar_init(accbar, 1);
+    tc::mbar_fence_init();
+  }
+  if (D < 128) {   // padded A rows [D, 128) are never written by the loaders: zero the planes once
+    for (int i = tid; i < F::PIPE / 16; i += THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == LOAD_WARPS) tc::tmem_alloc(tmem_slot, F::TMEM_COLS);
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < LOAD_WARPS) {
+    // ================= loader / converter =================
+    constexpr int TPW = F::TASKS / LOAD_WARPS;          // tasks per warp per stage (>= 1 for D >= 32... see launch)
+    const int e_l = lane >> 2, oq = lane & 3;
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % STAGES;
+      if (kc >= STAGES) tc::mbar_wait(&empty[s], ((kc / STAGES) - 1) & 1);
+      uint8_t* st = smem + s * F::STAGE;
+      const int64_t r0 = r_begin + (int64_t)kc * BK;
+      constexpr int NT = TPW > 0 ? TPW : 1;
+      float4 v[NT];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int task = warp * NT + t;
+        if (task < F::TASKS) {
+          const int mat = task / (4 * (D / 16)), rem = task % (4 * (D / 16));
+          const int eg = rem / (D / 16), og = rem % (D / 16);
+          const int64_t r = r0 + eg * 8 + e_l;
+          const float* src = mat == 0 ? Ag + r * lda : B + r * ldb;
+          v[t] = (r < r_end) ? __ldg(reinterpret_cast<const float4*>(src + (og * 4 + oq) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int task = warp * NT + t;
+        if (task < F::TASKS) {
+          const int mat = task / (4 * (D / 16)), rem = task % (4 * (D / 16));
+          const int eg = rem / (D / 16), og = rem % (D / 16);
+          const int o4 = og * 4 + oq, edge = eg * 8 + e_l;
+          uint2 hi, lo;
+          tc::split4(v[t], hi, lo);
+          const uint32_t lbo = mat == 0 ? F::LBO_A : F::LBO_B;
+          const int plane = mat == 0 ? F::A_PLANE : F::B_PLANE;
+          uint8_t* base = st + (mat == 0 ? 0 : 2 * F::A_PLANE);
+          const int off = (o4 >> 1) * (int)SBO + (edge >> 3) * (int)lbo + (edge & 7) * 16 + (o4 & 1) * 8;
+          *reinterpret_cast<uint2*>(base + off) = hi;
+          *reinterpret_cast<uint2*>(base + plane + off) = lo;
+        }
+      }
+      tc::fence_async_smem();
+      tc::mbar_arrive(&full[s]);
+    }
+    // ================= epilogue: TMEM -> partial tile in global =================
+    tc::mbar_wait(accbar, 0);
+    tc::fence_after_sync();
+    float* out = partials + ((int64_t)group * gridDim.x + cta) * D * D;
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int row_in_tile = q * 32 + lane;
+    // D = 256: warps 0-3 read M tile 0, warps 4-7 M tile 1.  D = 128: the two warp quads split the
+    // columns.  D <= 64: warps 0-3 read everything.
+    const int mt = (F::MT == 2) ? (warp >> 2) : 0;
+    const bool halves = (F::MT == 1) && (D >= 128);
+    const int c_begin = halves ? (warp >> 2) * (D / 2) : 0;
+    const int c_end = (F::MT == 2) ? D : (halves ? c_begin + D / 2 : ((warp >> 2) == 0 ? D : 0));
+    const int o = mt * 128 + row_in_tile;
+    if (nk > 0) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * D + c0), v);
+        if (o < D) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(out + (int64_t)o * D + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+    } else if (o < D) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 4)
+        *reinterpret_cast<float4*>(out + (int64_t)o * D + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else if (lane == 0) {
+    // ================= MMA issuer =================
+    constexpr uint32_t IDESC = tc::idesc_bf16_f32(128, D) | (1u << 15) | (1u << 16);   // A and B MN-major
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % STAGES;
+      tc::mbar_wait(&full[s], (kc / STAGES) & 1);
+      tc::fence_after_sync();
+      const uint32_t base = tc::smem_u32(smem + s * F::STAGE);
+#pragma unroll
+      for (int j = 0; j < BK / 16; ++j) {
+        const uint64_t b_hi = tc::smem_desc(base + 2 * F::A_PLANE + j * 2 * F::LBO_B, F::LBO_B, SBO);
+        const uint64_t b_lo = tc::smem_desc(base + 2 * F::A_PLANE + F::B_PLANE + j * 2 * F::LBO_B, F::LBO_B, SBO);
+#pragma unroll
+        for (int mt = 0; mt < F::MT; ++mt) {
+          const uint32_t ao = j * 2 * F::LBO_A + mt * 16 * SBO;
+          const uint64_t a_hi = tc::smem_desc(base + ao, F::LBO_A, SBO);
+          const uint64_t a_lo = tc::smem_desc(base + F::A_PLANE + ao, F::LBO_A, SBO);
+          const uint32_t d = tmem + (uint32_t)(mt * D);
+          tc::mma_bf16_ss(d, a_lo, b_hi, IDESC, (kc | j) != 0);
+          tc::mma_bf16_ss(d, a_hi, b_lo, IDESC, 1);
+          tc::mma_bf16_ss(d, a_hi, b_hi, IDESC, 1);
+        }
+      }
+      tc::mma_commit(&empty[s]);
+    }
+    tc::mma_commit(accbar);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == LOAD_WARPS) tc::tmem_dealloc(tmem, F::TMEM_COLS);
+}
+
+// out[g][o][i] = sum_c partials[g][c][o][i]  (fixed order)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partials, int ctas, int64_t tile, float* __restrict__ out,
+                                    int64_t ld_out, int D) {
+  const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int g = blockIdx.y;
+  if (idx >= tile) return;
+  const float* p = partials + (int64_t)g * ctas * tile + idx;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < ctas; ++c) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)c * tile));
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  const int64_t o = idx / D, i = idx % D;
+  *reinterpret_cast<float4*>(out + ((int64_t)g * D + o) * ld_out + i) = s;
+}
+
+inline int ctas_for(int64_t K, int groups) {
+  int per_group = kNumSMsWgrad / groups;
+  if (per_group < 1) per_group = 1;
+  const int64_t chunks = (K + BK - 1) / BK;
+  const int64_t want = (chunks + 3) / 4;          // at least ~4 pipeline stages of work per CTA
+  if (want < per_group) per_group = (int)(want < 1 ? 1 : want);
+  return per_group;
+}
+
+template <int D>
+int launch(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int groups, float* out, int64_t ld_out,
+           float* ws, cudaStream_t st) {
+  using F = Cfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_bf16x3_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
+    if (e != cudaSuccess) return record_cuda_error((int)e);
+    configured = true;
+  }
+  const int ctas = ctas_for(K, groups);
+  int64_t rows = (K + ctas - 1) / ctas;
+  rows = (rows + BK - 1) / BK * BK;               // slabs start on a stage boundary
+  wgrad_bf16x3_kernel<D><<<dim3(ctas, groups), THREADS, F::SMEM, st>>>(A, lda, B, ldb, K, (int)rows, ws);
+  int rc = check_launch();
+  if (rc != ALIGNN_OK) return rc;
+  const int64_t tile = (int64_t)D * D;
+  wgrad_reduce_kernel<<<dim3((unsigned)((tile / 4 + 255) / 256), groups), 256, 0, st>>>(ws, ctas, tile, out, ld_out, D);
+  return check_launch();
+}
+
+}  // namespace wgrad
+}  // namespace alignn
+
+extern "C" {
+
+size_t alignn_b200_wgrad_workspace_bytes(int64_t K, int D, int groups) {
+  if (K < 0 || groups < 1 || (D != 32 && D != 64 && D != 128 && D != 256)) return 0;
+  return (size_t)alignn::wgrad::ctas_for(K, groups) * groups * D * D * sizeof(float);
+}
+
+int alignn_b200_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int D, int groups, float* out,
+                      int64_t ld_out, void* workspace, size_t workspace_bytes, alignn_stream_t stream) {
+  using namespace alignn::wgrad;
+  if (K < 0 || groups < 1 || !out || ld_out < D || (ld_out % 4)) return ALIGNN_ERR_BAD_ARG;
+  if (D != 32 && D != 64 && D != 128 && D != 256) return ALIGNN_ERR_UNSUPPORTED_D;
+  if (K > 0 && (!A || !B || lda < (int64_t)groups * D || ldb < D || (lda % 4) || (ldb % 4))) return ALIGNN_ERR_BAD_ARG;
+  if (K >= ((int64_t)1 << 31) * BK) return ALIGNN_ERR_BAD_ARG;
+  if (!workspace || workspace_bytes < alignn_b200_wgrad_workspace_bytes(K, D, groups)) return ALIGNN_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = reinterpret_cast<float*>(workspace);
+  switch (D) {
+    case 256: return launch<256>(A, lda, B, ldb, K, groups, out, ld_out, ws, st);
+    case 128: return launch<128>(A, lda, B, ldb, K, groups, out, ld_out, ws, st);
+    case 64: return launch<64>(A, lda, B, ldb, K, groups, out, ld_out, ws, st);
+    default: return launch<32>(A, lda, B, ldb, K, groups, out, ld_out, ws, st);
+  }
+}
+
+}  // extern "C"

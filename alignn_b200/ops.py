@@ -210,3 +210,64 @@ class _SegmentMean(torch.autograd.Function):
 def segment_mean(x: torch.Tensor, graph_ptr: torch.Tensor) -> torch.Tensor:
     """Per-graph mean over node rows (dgl.nn.AvgPooling, alignn.py:325)."""
     return _SegmentMean.apply(x.contiguous(), graph_ptr)
+
+
+# ---- tensor-core Linear (tcgen05, bf16x3) --------------------------------------------------------
+class WeightImage:
+    """bf16 hi/lo image of a weight matrix W[N,K] (or of W^T when transpose=True) in UMMA core-matrix
+    order; valid until the weight changes (rebuilt every step in training)."""
+
+    __slots__ = ("buf", "N", "K")
+
+    def __init__(self, W: torch.Tensor, transpose: bool = False):
+        lib = _lib.load()
+        require_cuda(W)
+        if W.dim() != 2:
+            raise RuntimeError("WeightImage needs a 2-D weight")
+        self.N, self.K = (W.shape[1], W.shape[0]) if transpose else (W.shape[0], W.shape[1])
+        nbytes = int(lib.alignn_b200_gemm_weight_image_bytes(self.N, self.K))
+        if nbytes == 0:
+            raise RuntimeError(f"alignn_b200 GEMM: unsupported weight shape N={self.N}, K={self.K} (need multiples of 32)")
+        self.buf = torch.empty(nbytes, device=W.device, dtype=torch.uint8)
+        _lib.check(lib.alignn_b200_gemm_prepare_weights(ptr(W), self.N, self.K, W.stride(0), int(transpose), ptr_any(self.buf),
+                                                        stream_ptr()), "alignn_b200_gemm_prepare_weights")
+
+
+def ptr_any(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def gemm_nt(A: torch.Tensor, w: WeightImage, bias: Optional[torch.Tensor] = None,
+            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = A[M,K] @ W^T (+ bias) (+ residual) on tcgen05.  A may be a column slice (row stride >= K)."""
+    lib = _lib.load()
+    if A.dim() != 2 or A.stride(1) != 1 or A.shape[1] != w.K:
+        raise RuntimeError(f"gemm_nt: A must be [M,{w.K}] with unit column stride, got {tuple(A.shape)}/{A.stride()}")
+    for t in (A, bias, residual, out):
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+            raise RuntimeError("gemm_nt needs fp32 CUDA tensors")
+    M = A.shape[0]
+    if out is None:
+        out = torch.empty(M, w.N, device=A.device, dtype=torch.float32)
+    ldr = residual.stride(0) if residual is not None else 0
+    if residual is not None and (residual.stride(1) != 1 or residual.shape != (M, w.N)):
+        raise RuntimeError("gemm_nt: bad residual layout")
+    _lib.check(lib.alignn_b200_gemm_nt(ptr_any(A), A.stride(0), ptr_any(w.buf), M, w.N, w.K, ptr_any(bias), ptr_any(residual),
+                                        ldr, ptr_any(out), out.stride(0), stream_ptr()), "alignn_b200_gemm_nt")
+    return out
+
+
+def wgrad(A: torch.Tensor, B: torch.Tensor, groups: int = 1) -> torch.Tensor:
+    """out[g*D + o, i] = sum_r A[r, g*D + o] * B[r, i]  (dL/dW of a Linear: A = output grads, B = inputs)."""
+    lib = _lib.load()
+    require_cuda(A, B)
+    K, D = B.shape
+    if A.shape != (K, groups * D):
+        raise RuntimeError(f"wgrad: A must be [{K},{groups * D}], got {tuple(A.shape)}")
+    _check_d(D)
+    out = torch.empty(groups * D, D, device=A.device, dtype=torch.float32)
+    nbytes = int(lib.alignn_b200_wgrad_workspace_bytes(K, D, groups))
+    ws = torch.empty(max(nbytes, 16), device=A.device, dtype=torch.uint8)
+    _lib.check(lib.alignn_b200_wgrad(ptr(A), A.stride(0), ptr(B), B.stride(0), K, D, groups, ptr(out), D, ptr_any(ws), nbytes,
+                                      stream_ptr()), "alignn_b200_wgrad")
+    return out

@@ -185,6 +185,29 @@ int alignn_b200_gather_segment_sum(const float* Bh, const float* sigma, const in
                                    const int32_t* in_ptr, const int32_t* in_eid, int64_t Nn, int64_t Ne, int d,
                                    float* Sh, float* S, alignn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Linear layers on the 5th-gen tensor cores (tcgen05.mma, bf16x3 split operands, fp32 accumulate in
+ * TMEM; results agree with an fp32 GEMM to ~1e-5 relative):
+ *     C[M,N] = A[M,K] * W[N,K]^T (+ bias[N]) (+ R[M,N])
+ * Replaces the nn.Linear call sites alignn.py:98,99,101,104,110 (forward) and their data-gradient
+ * GEMMs.  W is first converted once per step to a bf16 hi/lo image (`gemm_prepare_weights`;
+ * `transpose != 0` takes W^T of a [K,N] array, which is what the data-gradient GEMMs need).
+ * Constraints: K % 32 == 0, N % 32 == 0, lda/ldc/ldr % 4 == 0 (16-byte rows).
+ * ---------------------------------------------------------------------------------------- */
+size_t alignn_b200_gemm_weight_image_bytes(int N, int K);   /* 0 if the shape is unsupported */
+int alignn_b200_gemm_prepare_weights(const float* W, int N, int K, int64_t ldw, int transpose, void* image,
+                                     alignn_stream_t stream);
+int alignn_b200_gemm_nt(const float* A, int64_t lda, const void* w_image, int64_t M, int N, int K, const float* bias,
+                        const float* R, int64_t ldr, float* C, int64_t ldc, alignn_stream_t stream);
+
+/* Weight gradients on the tensor cores (split-K over the batch rows, deterministic two-stage sum):
+ *     out[g*D + o, i] = sum_{r < K} A[r, g*D + o] * B[r, i]        g < groups,  o, i < D
+ * i.e. dL/dW = GM^T y (groups = 1) and dL/dWcat = GP^T x (groups = 4) of SURVEY.md App. B.
+ * `workspace` holds the per-CTA partial tiles (size from alignn_b200_wgrad_workspace_bytes). */
+size_t alignn_b200_wgrad_workspace_bytes(int64_t K, int D, int groups);
+int alignn_b200_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int D, int groups, float* out,
+                      int64_t ld_out, void* workspace, size_t workspace_bytes, alignn_stream_t stream);
+
 /* Per-graph mean over node rows (dgl.nn.AvgPooling, alignn.py:325) and its backward. */
 int alignn_b200_segment_mean(const float* x, const int32_t* graph_ptr /*[B+1]*/, int64_t B, int d, float* out,
                              alignn_stream_t stream);

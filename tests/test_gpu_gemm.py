@@ -1,0 +1,81 @@
+"""GPU (-m gpu): the tcgen05 bf16x3 Linear kernel against an fp64 matmul.
+
+Tolerance 2e-5 relative to the output scale: the bf16x3 split drops terms of relative size
+<= 3*2^-18 per product (tc_common.cuh), ~4e-6 rms on a K=256 dot product."""
+import pytest
+import torch
+
+from alignn_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ref(A, W, bias, R):
+    out = A.double() @ W.double().t()
+    if bias is not None:
+        out += bias.double()
+    if R is not None:
+        out += R.double()
+    return out
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 256, 256), (1000, 256, 256), (1920, 1024, 256),
+                                   (23040, 256, 1024), (333, 64, 64), (77, 32, 32), (5000, 128, 128)])
+def test_gemm_nt_matches_fp64(M, N, K):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    R = torch.randn(M, N, generator=g).to(DEV)
+    img = ops.WeightImage(W)
+    for b, r in ((None, None), (bias, None), (bias, R)):
+        out = ops.gemm_nt(A, img, b, r)
+        ref = _ref(A, W, b, r)
+        err = (out.double() - ref).abs().max().item()
+        assert err <= 2e-5 * ref.abs().max().item(), (M, N, K, err, ref.abs().max().item())
+
+
+def test_gemm_transposed_weight_and_strided_input():
+    """Data-gradient form: C = G[M,N'] @ W[N',K'] uses the image of W^T; A may be a column slice."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    G = torch.randn(700, 1024, generator=g).to(DEV)
+    W = (torch.randn(256, 256, generator=g) / 16).to(DEV)            # Linear weight [out, in]
+    img_t = ops.WeightImage(W, transpose=True)                        # acts as W^T: N = in, K = out
+    A = G[:, 256:512]                                                 # row stride 1024
+    out = ops.gemm_nt(A, img_t)
+    ref = A.double() @ W.double()
+    assert (out.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+
+
+def test_gemm_extreme_magnitudes():
+    """bf16 has fp32's exponent range: large / tiny activations keep the same relative accuracy."""
+    g = torch.Generator(device="cpu").manual_seed(9)
+    for scale in (1e-20, 1e12):
+        A = (torch.randn(256, 256, generator=g) * scale).to(DEV)
+        W = (torch.randn(256, 256, generator=g) / 16).to(DEV)
+        out = ops.gemm_nt(A, ops.WeightImage(W))
+        ref = A.double() @ W.double().t()
+        assert (out.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+
+
+def test_gemm_rejects_bad_shapes():
+    W = torch.zeros(48, 64, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.WeightImage(W)
+    img = ops.WeightImage(torch.zeros(64, 64, device=DEV))
+    with pytest.raises(RuntimeError):
+        ops.gemm_nt(torch.zeros(8, 32, device=DEV), img)
+
+
+@pytest.mark.parametrize("K,D,groups", [(32, 256, 1), (1000, 256, 1), (23040, 256, 4), (276480, 256, 1), (5000, 128, 4),
+                                        (777, 64, 1), (130, 32, 4), (3, 256, 1)])
+def test_wgrad_matches_fp64(K, D, groups):
+    g = torch.Generator(device="cpu").manual_seed(K + D)
+    A = torch.randn(K, groups * D, generator=g).to(DEV)
+    B = torch.randn(K, D, generator=g).to(DEV)
+    out = ops.wgrad(A, B, groups)
+    ref = A.double().t() @ B.double()
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 2e-5 * ref.abs().max().item(), (K, D, groups, err, ref.abs().max().item())
+    assert torch.equal(out, ops.wgrad(A, B, groups))          # deterministic split-K
