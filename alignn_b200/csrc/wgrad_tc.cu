@@ -60,7 +60,7 @@ wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __res
   const float* Ag = A + (int64_t)group * D;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], LOADERS); tc::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], LOAD_WARPS); tc::mbar_init(&empty[s], 1); }
     tc::mbar_init(accbar, 1);
     tc::mbar_fence_init();
   }
@@ -77,25 +77,26 @@ wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __res
   if (warp < LOAD_WARPS) {
     // ================= loader / converter =================
     constexpr int TPW = F::TASKS / LOAD_WARPS;          // tasks per warp per stage (>= 1 for D >= 32... see launch)
-    const int e_l = lane >> 2, oq = lane & 3;
-    for (int kc = 0; kc < nk; ++kc) {
-      const int s = kc % STAGES;
-      if (kc >= STAGES) tc::mbar_wait(&empty[s], ((kc / STAGES) - 1) & 1);
-      uint8_t* st = smem + s * F::STAGE;
+    // half-warp = 8 contraction rows x 2 adjacent float4 -> one 128-byte core matrix: conflict-free 64-bit stores
+    const int e_l = (lane >> 1) & 7, oq = (lane >> 4) * 2 + (lane & 1);
+    constexpr int NT = TPW > 0 ? TPW : 1;
+    auto load_chunk = [&](float4 (&v)[NT], int kc) {
       const int64_t r0 = r_begin + (int64_t)kc * BK;
-      constexpr int NT = TPW > 0 ? TPW : 1;
-      float4 v[NT];
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
         const int task = warp * NT + t;
-        if (task < F::TASKS) {
-          const int mat = task / (4 * (D / 16)), rem = task % (4 * (D / 16));
-          const int eg = rem / (D / 16), og = rem % (D / 16);
-          const int64_t r = r0 + eg * 8 + e_l;
-          const float* src = mat == 0 ? Ag + r * lda : B + r * ldb;
-          v[t] = (r < r_end) ? __ldg(reinterpret_cast<const float4*>(src + (og * 4 + oq) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        const int mat = task / (4 * (D / 16)), rem = task % (4 * (D / 16));
+        const int eg = rem / (D / 16), og = rem % (D / 16);
+        const int64_t r = r0 + eg * 8 + e_l;
+        const float* src = mat == 0 ? Ag + r * lda : B + r * ldb;
+        v[t] = (task < F::TASKS && r < r_end) ? __ldcs(reinterpret_cast<const float4*>(src + (og * 4 + oq) * 4))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    };
+    auto store_chunk = [&](const float4 (&v)[NT], int kc) {
+      const int s = kc % STAGES;
+      if (kc >= STAGES) tc::mbar_wait(&empty[s], ((kc / STAGES) - 1) & 1);
+      uint8_t* st = smem + s * F::STAGE;
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
         const int task = warp * NT + t;
@@ -114,7 +115,19 @@ wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __res
         }
       }
       tc::fence_async_smem();
-      tc::mbar_arrive(&full[s]);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&full[s]);          // one arrival per warp
+    };
+    // double-buffered in registers: the loads of chunk k+1 are in flight while chunk k is converted
+    float4 b0[NT], b1[NT];
+    if (nk > 0) load_chunk(b0, 0);
+    for (int kc = 0; kc < nk; kc += 2) {
+      if (kc + 1 < nk) load_chunk(b1, kc + 1);
+      store_chunk(b0, kc);
+      if (kc + 1 < nk) {
+        if (kc + 2 < nk) load_chunk(b0, kc + 2);
+        store_chunk(b1, kc + 1);
+      }
     }
     // ================= epilogue: TMEM -> partial tile in global =================
     tc::mbar_wait(accbar, 0);
