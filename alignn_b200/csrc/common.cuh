@@ -94,6 +94,28 @@ __device__ __forceinline__ void row_mean_rstd(const float (&v)[RowCfg<D>::VPL], 
   rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
 }
 
+// acc[lane layout] += v, for per-warp accumulator rows kept in shared memory (frees registers in the
+// big backward kernel).  Each lane only ever touches its own channels: no conflicts, no atomics.
+template <int D>
+__device__ __forceinline__ void smem_row_add(float* __restrict__ acc_row, const float (&v)[RowCfg<D>::VPL], int lane) {
+  using C = RowCfg<D>;
+#pragma unroll
+  for (int c = 0; c < C::CH; ++c) {
+    float* p = acc_row + c * 32 * C::W + lane * C::W;
+    if constexpr (C::W == 4) {
+      float4 t = *reinterpret_cast<float4*>(p);
+      t.x += v[c * 4 + 0]; t.y += v[c * 4 + 1]; t.z += v[c * 4 + 2]; t.w += v[c * 4 + 3];
+      *reinterpret_cast<float4*>(p) = t;
+    } else if constexpr (C::W == 2) {
+      float2 t = *reinterpret_cast<float2*>(p);
+      t.x += v[c * 2 + 0]; t.y += v[c * 2 + 1];
+      *reinterpret_cast<float2*>(p) = t;
+    } else {
+      *p += v[c];
+    }
+  }
+}
+
 // Sum the per-warp accumulators of a block in a fixed order and write one partial row.
 // acc: NQ quantities of VPL per lane.  out row layout: [NQ][D].  smem: [kWarpsPerBlock][D].
 template <int D, int NQ>

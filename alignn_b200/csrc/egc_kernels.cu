@@ -135,61 +135,65 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
 // backward, GM = dL/dm, GP[:, 2d:3d] = sum over in-edges (dL/d e_dst), GP[:, 3d:4d] = dL/dx'.
 // partials row: {sum gu_e*xhat_e, sum gu_e, sum gu_n*xhat_n, sum gu_n, sum gD, sum gB}
 // =============================================================================================
-template <int D>
+template <int D, int mode>
 __device__ __forceinline__ void norm_backward_row(const float (&r)[RowCfg<D>::VPL], const float (&go)[RowCfg<D>::VPL],
-                                                  int mode, float ln_eps,
+                                                  float ln_eps,
                                                   const float (&w)[RowCfg<D>::VPL], const float (&b)[RowCfg<D>::VPL],
                                                   const float (&mu)[RowCfg<D>::VPL], const float (&rs)[RowCfg<D>::VPL],
                                                   const float (&c1)[RowCfg<D>::VPL], const float (&c2)[RowCfg<D>::VPL],
-                                                  float (&gr)[RowCfg<D>::VPL], float (&acc_gw)[RowCfg<D>::VPL],
-                                                  float (&acc_gb)[RowCfg<D>::VPL]) {
+                                                  float (&gr)[RowCfg<D>::VPL], float* __restrict__ acc_gw,
+                                                  float* __restrict__ acc_gb, int lane) {
   constexpr int V = RowCfg<D>::VPL;
-  if (mode == ALIGNN_NORM_LAYER) {
+  if constexpr (mode == ALIGNN_NORM_LAYER) {
     float mean, rstd;
     row_mean_rstd<D>(r, ln_eps, mean, rstd);
-    float xh[V], gxh[V], sa = 0.f, sb = 0.f;
+    float xh[V], gxh[V], t0[V], t1[V], sa = 0.f, sb = 0.f;
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       xh[k] = (r[k] - mean) * rstd;
       const float gu = go[k] * dsilu_(xh[k] * w[k] + b[k]);
-      acc_gw[k] += gu * xh[k];
-      acc_gb[k] += gu;
+      t0[k] = gu * xh[k];
+      t1[k] = gu;
       gxh[k] = gu * w[k];
       sa += gxh[k];
       sb += gxh[k] * xh[k];
     }
+    smem_row_add<D>(acc_gw, t0, lane);
+    smem_row_add<D>(acc_gb, t1, lane);
     sa = warp_sum(sa) * (1.f / D);
     sb = warp_sum(sb) * (1.f / D);
 #pragma unroll
     for (int k = 0; k < V; ++k) gr[k] = rstd * (gxh[k] - sa - xh[k] * sb);
   } else {
     // w = scale, b = shift; xhat = (r - mean_c) * rstd_c
+    float t0[V], t1[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       const float gu = go[k] * dsilu_(r[k] * w[k] + b[k]);
       const float xh = (r[k] - mu[k]) * rs[k];
-      acc_gw[k] += gu * xh;
-      acc_gb[k] += gu;
+      t0[k] = gu * xh;
+      t1[k] = gu;
       gr[k] = (mode == ALIGNN_NORM_STATS) ? w[k] * (gu - c1[k] - xh * c2[k]) : w[k] * gu;
     }
+    smem_row_add<D>(acc_gw, t0, lane);
+    smem_row_add<D>(acc_gb, t1, lane);
   }
 }
 
-template <int D>
+template <int D, int NORM>   // NORM: the norm mode of both bn_nodes and bn_edges (compile-time: unused vectors vanish)
 __global__ void __launch_bounds__(kThreads)
 egc_backward_dst_kernel(alignn_b200_egc_bwd_args a) {
   using C = RowCfg<D>;
   constexpr int V = C::VPL;
-  __shared__ float red[kWarpsPerBlock * D];
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  // per-warp partial sums live in shared memory (6 rows of D per warp): keeping them in registers cost 48
+  // registers per thread and halved the resident warps of this HBM-latency-bound kernel
+  __shared__ float sacc[kWarpsPerBlock * 6 * D];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-
-  float acc[6][V];
-#pragma unroll
-  for (int q = 0; q < 6; ++q)
-#pragma unroll
-    for (int i = 0; i < V; ++i) acc[q][i] = 0.f;
+  float* acc = sacc + wib * 6 * D;     // acc + q*D = row q of this warp
+  for (int i = lane; i < 6 * D; i += 32) acc[i] = 0.f;
+  __syncwarp();
 
   for (int64_t v = warp0; v < a.Nn; v += nwarps) {
     float gsh[V], gs[V];
@@ -201,7 +205,7 @@ egc_backward_dst_kernel(alignn_b200_egc_bwd_args a) {
       float xp[V], go[V], gxp[V], sv[V], hv[V];
       ld_row<D, false>(xp, a.XP + v * D, lane);
       ld_row<D, false>(go, a.gx_out + v * D, lane);
-      norm_backward_row<D>(xp, go, a.norm_nodes, a.ln_eps, nw, nb, nmu, nrs, nc1, nc2, gxp, acc[2], acc[3]);
+      norm_backward_row<D, NORM>(xp, go, a.ln_eps, nw, nb, nmu, nrs, nc1, nc2, gxp, acc + 2 * D, acc + 3 * D, lane);
       st_row<D, false>(a.GP + v * 4 * D + 3 * D, gxp, lane);
       ld_row<D, false>(sv, a.S + v * D, lane);
       ld_row<D, false>(hv, a.H + v * D, lane);
@@ -210,8 +214,8 @@ egc_backward_dst_kernel(alignn_b200_egc_bwd_args a) {
         const float inv = 1.f / (sv[k] + a.gate_eps);
         gsh[k] = gxp[k] * inv;
         gs[k] = -gxp[k] * hv[k] * inv;
-        acc[4][k] += gxp[k];
       }
+      smem_row_add<D>(acc + 4 * D, gxp, lane);
       st_row<D, false>(a.GSh + v * D, gsh, lane);
     }
     float ew[V], eb[V], emu[V], ers[V], ec1[V], ec2[V];
@@ -238,7 +242,7 @@ egc_backward_dst_kernel(alignn_b200_egc_bwd_args a) {
         if (a.gy_out) {
           float go[V];
           ld_row<D, true>(go, a.gy_out + e * D, lane);
-          norm_backward_row<D>(m, go, a.norm_edges, a.ln_eps, ew, eb, emu, ers, ec1, ec2, gm, acc[0], acc[1]);
+          norm_backward_row<D, NORM>(m, go, a.ln_eps, ew, eb, emu, ers, ec1, ec2, gm, acc, acc + D, lane);
         } else {
 #pragma unroll
           for (int k = 0; k < V; ++k) gm[k] = 0.f;
@@ -253,10 +257,18 @@ egc_backward_dst_kernel(alignn_b200_egc_bwd_args a) {
       }
     }
     st_row<D, false>(a.GP + v * 4 * D + 2 * D, accB, lane);
-#pragma unroll
-    for (int k = 0; k < V; ++k) acc[5][k] += accB[k];
+    smem_row_add<D>(acc + 5 * D, accB, lane);
   }
-  if (a.partials) block_reduce_to_partials<D, 6>(acc, a.partials + (int64_t)blockIdx.x * 6 * D, red);
+  __syncthreads();
+  if (a.partials) {   // fixed-order sum over the block's warps -> one partial row
+    float* out_row = a.partials + (int64_t)blockIdx.x * 6 * D;
+    for (int i = threadIdx.x; i < 6 * D; i += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarpsPerBlock; ++w) t += sacc[w * 6 * D + i];
+      out_row[i] = t;
+    }
+  }
 }
 
 // =============================================================================================
@@ -630,7 +642,15 @@ int alignn_b200_egc_backward(const alignn_b200_egc_bwd_args* a) {
   }
   cudaStream_t st = (cudaStream_t)a->stream;
   const int grid = grid_for_rows(a->Nn);
-  DISPATCH_D(a->d, alignn::egc_backward_dst_kernel<D><<<grid, alignn::kThreads, 0, st>>>(*a));
+  if (a->norm_nodes != a->norm_edges) return ALIGNN_ERR_BAD_ARG;   // both norms of a conv are of one kind (alignn.py:71-76)
+  switch (a->norm_nodes) {
+    case ALIGNN_NORM_LAYER:
+      DISPATCH_D(a->d, alignn::egc_backward_dst_kernel<D, ALIGNN_NORM_LAYER><<<grid, alignn::kThreads, 0, st>>>(*a)); break;
+    case ALIGNN_NORM_AFFINE:
+      DISPATCH_D(a->d, alignn::egc_backward_dst_kernel<D, ALIGNN_NORM_AFFINE><<<grid, alignn::kThreads, 0, st>>>(*a)); break;
+    default:
+      DISPATCH_D(a->d, alignn::egc_backward_dst_kernel<D, ALIGNN_NORM_STATS><<<grid, alignn::kThreads, 0, st>>>(*a)); break;
+  }
   int rc = check_launch();
   if (rc != ALIGNN_OK) return rc;
   DISPATCH_D(a->d, alignn::egc_backward_src_kernel<D><<<grid, alignn::kThreads, 0, st>>>(*a, a->partials_src));

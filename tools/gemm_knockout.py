@@ -31,7 +31,7 @@ def t(flags):
     return e0.elapsed_time(e1) / 5 * 1e3
 
 
-for name, f in [("full", 0), ("full, relaxed arrive", 1024), ("full, relaxed arrive, no C", 1024 + 4), ("no C", 4)]:
+for name, f in [("full (L2 tile prefetch)", 0), ("full, no L2 prefetch", 2048), ("no C", 4), ("no C, no L2 prefetch", 4 + 2048)]:
     print(f"{name:40s} {t(f):8.1f} us")
 for Mx in (276480 // 4, 276480 // 16, 128 * 148):
     A = torch.randn(Mx, K, device=dev)
