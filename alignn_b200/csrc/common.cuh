@@ -94,6 +94,25 @@ __device__ __forceinline__ void row_mean_rstd(const float (&v)[RowCfg<D>::VPL], 
   rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
 }
 
+// row held in SHARED memory (per-channel parameter vectors staged once per block) -> lane layout
+template <int D>
+__device__ __forceinline__ void ld_srow(float (&v)[RowCfg<D>::VPL], const float* __restrict__ row, int lane) {
+  using C = RowCfg<D>;
+#pragma unroll
+  for (int c = 0; c < C::CH; ++c) {
+    const float* p = row + c * 32 * C::W + lane * C::W;
+    if constexpr (C::W == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(p);
+      v[c * 4 + 0] = t.x; v[c * 4 + 1] = t.y; v[c * 4 + 2] = t.z; v[c * 4 + 3] = t.w;
+    } else if constexpr (C::W == 2) {
+      const float2 t = *reinterpret_cast<const float2*>(p);
+      v[c * 2 + 0] = t.x; v[c * 2 + 1] = t.y;
+    } else {
+      v[c] = *p;
+    }
+  }
+}
+
 // acc[lane layout] += v, for per-warp accumulator rows kept in shared memory (frees registers in the
 // big backward kernel).  Each lane only ever touches its own channels: no conflicts, no atomics.
 template <int D>

@@ -135,48 +135,61 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
 // backward, GM = dL/dm, GP[:, 2d:3d] = sum over in-edges (dL/d e_dst), GP[:, 3d:4d] = dL/dx'.
 // partials row: {sum gu_e*xhat_e, sum gu_e, sum gu_n*xhat_n, sum gu_n, sum gD, sum gB}
 // =============================================================================================
+// vecs: 6 per-channel vectors in shared memory at stride D: {w, b, mean, rstd, c1, c2} (meaning per mode in
+// include/alignn_b200.h).  They are re-read from shared memory at every use instead of living in registers.
 template <int D, int mode>
 __device__ __forceinline__ void norm_backward_row(const float (&r)[RowCfg<D>::VPL], const float (&go)[RowCfg<D>::VPL],
-                                                  float ln_eps,
-                                                  const float (&w)[RowCfg<D>::VPL], const float (&b)[RowCfg<D>::VPL],
-                                                  const float (&mu)[RowCfg<D>::VPL], const float (&rs)[RowCfg<D>::VPL],
-                                                  const float (&c1)[RowCfg<D>::VPL], const float (&c2)[RowCfg<D>::VPL],
+                                                  float ln_eps, const float* __restrict__ vecs,
                                                   float (&gr)[RowCfg<D>::VPL], float* __restrict__ acc_gw,
                                                   float* __restrict__ acc_gb, int lane) {
   constexpr int V = RowCfg<D>::VPL;
+  float w[V], b[V];
+  ld_srow<D>(w, vecs, lane);
+  ld_srow<D>(b, vecs + D, lane);
   if constexpr (mode == ALIGNN_NORM_LAYER) {
     float mean, rstd;
     row_mean_rstd<D>(r, ln_eps, mean, rstd);
-    float xh[V], gxh[V], t0[V], t1[V], sa = 0.f, sb = 0.f;
+    float xh[V], gxh[V], t1[V], sa = 0.f, sb = 0.f;
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       xh[k] = (r[k] - mean) * rstd;
       const float gu = go[k] * dsilu_(xh[k] * w[k] + b[k]);
-      t0[k] = gu * xh[k];
       t1[k] = gu;
       gxh[k] = gu * w[k];
       sa += gxh[k];
       sb += gxh[k] * xh[k];
     }
-    smem_row_add<D>(acc_gw, t0, lane);
     smem_row_add<D>(acc_gb, t1, lane);
+#pragma unroll
+    for (int k = 0; k < V; ++k) t1[k] *= xh[k];
+    smem_row_add<D>(acc_gw, t1, lane);
     sa = warp_sum(sa) * (1.f / D);
     sb = warp_sum(sb) * (1.f / D);
 #pragma unroll
     for (int k = 0; k < V; ++k) gr[k] = rstd * (gxh[k] - sa - xh[k] * sb);
   } else {
     // w = scale, b = shift; xhat = (r - mean_c) * rstd_c
-    float t0[V], t1[V];
+    float mu[V], rs[V], t0[V], t1[V];
+    ld_srow<D>(mu, vecs + 2 * D, lane);
+    ld_srow<D>(rs, vecs + 3 * D, lane);
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       const float gu = go[k] * dsilu_(r[k] * w[k] + b[k]);
       const float xh = (r[k] - mu[k]) * rs[k];
       t0[k] = gu * xh;
       t1[k] = gu;
-      gr[k] = (mode == ALIGNN_NORM_STATS) ? w[k] * (gu - c1[k] - xh * c2[k]) : w[k] * gu;
+      gr[k] = w[k] * gu;
+      mu[k] = xh;
     }
     smem_row_add<D>(acc_gw, t0, lane);
     smem_row_add<D>(acc_gb, t1, lane);
+    if constexpr (mode == ALIGNN_NORM_STATS) {
+      float c1[V], c2[V];
+      ld_srow<D>(c1, vecs + 4 * D, lane);
+      ld_srow<D>(c2, vecs + 5 * D, lane);
+#pragma unroll
+      for (int k = 0; k < V; ++k) gr[k] -= w[k] * (c1[k] + mu[k] * c2[k]);
+    }
   }
 }
 
@@ -187,7 +200,17 @@ egc_backward_dst_kernel(alignn_b200_egc_bwd_args a) {
   constexpr int V = C::VPL;
   // per-warp partial sums live in shared memory (6 rows of D per warp): keeping them in registers cost 48
   // registers per thread and halved the resident warps of this HBM-latency-bound kernel
-  __shared__ float sacc[kWarpsPerBlock * 6 * D];
+  extern __shared__ __align__(16) float dyn_smem[];
+  float* sacc = dyn_smem;                                  // [kWarpsPerBlock][6][D]
+  float* nvec = dyn_smem + kWarpsPerBlock * 6 * D;         // node norm vectors  [6][D]
+  float* evec = nvec + 6 * D;                              // edge norm vectors  [6][D]
+  {
+    const float* srcs[12] = {a.n_w, a.n_b, a.n_mean, a.n_rstd, a.n_c1, a.n_c2, a.e_w, a.e_b, a.e_mean, a.e_rstd, a.e_c1, a.e_c2};
+#pragma unroll
+    for (int q = 0; q < 12; ++q)
+      for (int i = threadIdx.x; i < D; i += blockDim.x) nvec[q * D + i] = srcs[q] ? srcs[q][i] : 0.f;
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
@@ -198,14 +221,10 @@ egc_backward_dst_kernel(alignn_b200_egc_bwd_args a) {
   for (int64_t v = warp0; v < a.Nn; v += nwarps) {
     float gsh[V], gs[V];
     {  // node side
-      float nw[V], nb[V], nmu[V], nrs[V], nc1[V], nc2[V];
-      ld_vec<D>(nw, a.n_w, lane); ld_vec<D>(nb, a.n_b, lane);
-      ld_vec<D>(nmu, a.n_mean, lane); ld_vec<D>(nrs, a.n_rstd, lane);
-      ld_vec<D>(nc1, a.n_c1, lane); ld_vec<D>(nc2, a.n_c2, lane);
       float xp[V], go[V], gxp[V], sv[V], hv[V];
       ld_row<D, false>(xp, a.XP + v * D, lane);
       ld_row<D, false>(go, a.gx_out + v * D, lane);
-      norm_backward_row<D, NORM>(xp, go, a.ln_eps, nw, nb, nmu, nrs, nc1, nc2, gxp, acc + 2 * D, acc + 3 * D, lane);
+      norm_backward_row<D, NORM>(xp, go, a.ln_eps, nvec, gxp, acc + 2 * D, acc + 3 * D, lane);
       st_row<D, false>(a.GP + v * 4 * D + 3 * D, gxp, lane);
       ld_row<D, false>(sv, a.S + v * D, lane);
       ld_row<D, false>(hv, a.H + v * D, lane);
@@ -218,10 +237,6 @@ egc_backward_dst_kernel(alignn_b200_egc_bwd_args a) {
       smem_row_add<D>(acc + 4 * D, gxp, lane);
       st_row<D, false>(a.GSh + v * D, gsh, lane);
     }
-    float ew[V], eb[V], emu[V], ers[V], ec1[V], ec2[V];
-    ld_vec<D>(ew, a.e_w, lane); ld_vec<D>(eb, a.e_b, lane);
-    ld_vec<D>(emu, a.e_mean, lane); ld_vec<D>(ers, a.e_rstd, lane);
-    ld_vec<D>(ec1, a.e_c1, lane); ld_vec<D>(ec2, a.e_c2, lane);
     float accB[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) accB[k] = 0.f;
@@ -242,7 +257,7 @@ egc_backward_dst_kernel(alignn_b200_egc_bwd_args a) {
         if (a.gy_out) {
           float go[V];
           ld_row<D, true>(go, a.gy_out + e * D, lane);
-          norm_backward_row<D, NORM>(m, go, a.ln_eps, ew, eb, emu, ers, ec1, ec2, gm, acc, acc + D, lane);
+          norm_backward_row<D, NORM>(m, go, a.ln_eps, evec, gm, acc, acc + D, lane);
         } else {
 #pragma unroll
           for (int k = 0; k < V; ++k) gm[k] = 0.f;
@@ -643,14 +658,24 @@ int alignn_b200_egc_backward(const alignn_b200_egc_bwd_args* a) {
   cudaStream_t st = (cudaStream_t)a->stream;
   const int grid = grid_for_rows(a->Nn);
   if (a->norm_nodes != a->norm_edges) return ALIGNN_ERR_BAD_ARG;   // both norms of a conv are of one kind (alignn.py:71-76)
+#define LAUNCH_BWD_DST(NORM)                                                                                   \
+  DISPATCH_D(a->d, {                                                                                           \
+    const size_t smem_bytes = (size_t)(alignn::kWarpsPerBlock * 6 + 12) * D * sizeof(float);                   \
+    static bool configured = false;                                                                            \
+    if (!configured) {                                                                                         \
+      cudaError_t e = cudaFuncSetAttribute(alignn::egc_backward_dst_kernel<D, NORM>,                           \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);      \
+      if (e != cudaSuccess) return alignn::record_cuda_error((int)e);                                          \
+      configured = true;                                                                                       \
+    }                                                                                                          \
+    alignn::egc_backward_dst_kernel<D, NORM><<<grid, alignn::kThreads, smem_bytes, st>>>(*a);                  \
+  })
   switch (a->norm_nodes) {
-    case ALIGNN_NORM_LAYER:
-      DISPATCH_D(a->d, alignn::egc_backward_dst_kernel<D, ALIGNN_NORM_LAYER><<<grid, alignn::kThreads, 0, st>>>(*a)); break;
-    case ALIGNN_NORM_AFFINE:
-      DISPATCH_D(a->d, alignn::egc_backward_dst_kernel<D, ALIGNN_NORM_AFFINE><<<grid, alignn::kThreads, 0, st>>>(*a)); break;
-    default:
-      DISPATCH_D(a->d, alignn::egc_backward_dst_kernel<D, ALIGNN_NORM_STATS><<<grid, alignn::kThreads, 0, st>>>(*a)); break;
+    case ALIGNN_NORM_LAYER: LAUNCH_BWD_DST(ALIGNN_NORM_LAYER); break;
+    case ALIGNN_NORM_AFFINE: LAUNCH_BWD_DST(ALIGNN_NORM_AFFINE); break;
+    default: LAUNCH_BWD_DST(ALIGNN_NORM_STATS); break;
   }
+#undef LAUNCH_BWD_DST
   int rc = check_launch();
   if (rc != ALIGNN_OK) return rc;
   DISPATCH_D(a->d, alignn::egc_backward_src_kernel<D><<<grid, alignn::kThreads, 0, st>>>(*a, a->partials_src));
