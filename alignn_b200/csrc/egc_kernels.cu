@@ -22,24 +22,31 @@ __device__ __forceinline__ float dsilu_(float u) { float s = sigmoidf_(u); retur
 // Forward
 // =============================================================================================
 template <int D>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 egc_forward_kernel(alignn_b200_egc_fwd_args a) {
   using C = RowCfg<D>;
   constexpr int V = C::VPL;
-  __shared__ float red[kWarpsPerBlock * D];
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  // norm vectors {n_w, n_b, e_w, e_b} and (STATS mode) the per-warp partial sums live in shared memory so
+  // (the kernel sits at the L2-fabric limit -- G stream + row gathers -- so 2 blocks/SM are enough;
+  //  3 blocks/SM were measured no faster)
+  extern __shared__ __align__(16) float dyn_smem[];
+  float* vec = dyn_smem;                       // [4][D]
+  float* sacc = dyn_smem + 4 * D;              // [kWarpsPerBlock][4][D]   {sum m, sum m^2, sum x', sum x'^2}
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
   const bool train = a.M != nullptr;
-
-  float nw[V], nb[V], ew[V], eb[V];
-  ld_vec<D>(nw, a.n_w, lane); ld_vec<D>(nb, a.n_b, lane);
-  ld_vec<D>(ew, a.e_w, lane); ld_vec<D>(eb, a.e_b, lane);
-  float st[4][V];  // STATS mode: {sum m, sum m^2, sum x', sum x'^2}
+  const bool stats = a.partials != nullptr;
+  {
+    const float* srcs[4] = {a.n_w, a.n_b, a.e_w, a.e_b};
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
-#pragma unroll
-    for (int i = 0; i < V; ++i) st[q][i] = 0.f;
+    for (int q = 0; q < 4; ++q)
+      for (int i = threadIdx.x; i < D; i += blockDim.x) vec[q * D + i] = srcs[q] ? srcs[q][i] : 0.f;
+  }
+  float* st = sacc + wib * 4 * D;
+  if (stats)
+    for (int i = lane; i < 4 * D; i += 32) st[i] = 0.f;
+  __syncthreads();
 
   for (int64_t v = warp0; v < a.Nn; v += nwarps) {
     const int p0 = a.in_ptr[v], p1 = a.in_ptr[v + 1];
@@ -71,10 +78,14 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
         }
         if (train) st_row<D, true>(a.M + e * D, m, lane);
         if (a.norm_edges == ALIGNN_NORM_STATS) {
+          smem_row_add<D>(st, m, lane);
 #pragma unroll
-          for (int k = 0; k < V; ++k) { st[0][k] += m[k]; st[1][k] += m[k] * m[k]; }
+          for (int k = 0; k < V; ++k) m[k] *= m[k];
+          smem_row_add<D>(st + D, m, lane);
         } else if (a.y_out) {
-          float o[V];
+          float o[V], ew[V], eb[V];
+          ld_srow<D>(ew, vec + 2 * D, lane);
+          ld_srow<D>(eb, vec + 3 * D, lane);
           if (a.norm_edges == ALIGNN_NORM_LAYER) {
             float mean, rstd;
             row_mean_rstd<D>(m, a.ln_eps, mean, rstd);
@@ -105,10 +116,14 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
       st_row<D, false>(a.H + v * D, h, lane);
     }
     if (a.norm_nodes == ALIGNN_NORM_STATS) {
+      smem_row_add<D>(st + 2 * D, xp, lane);
 #pragma unroll
-      for (int k = 0; k < V; ++k) { st[2][k] += xp[k]; st[3][k] += xp[k] * xp[k]; }
+      for (int k = 0; k < V; ++k) xp[k] *= xp[k];
+      smem_row_add<D>(st + 3 * D, xp, lane);
     } else {
-      float o[V];
+      float o[V], nw[V], nb[V];
+      ld_srow<D>(nw, vec, lane);
+      ld_srow<D>(nb, vec + D, lane);
       if (a.norm_nodes == ALIGNN_NORM_LAYER) {
         float mean, rstd;
         row_mean_rstd<D>(xp, a.ln_eps, mean, rstd);
@@ -127,7 +142,16 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
       st_row<D, false>(a.x_out + v * D, o, lane);
     }
   }
-  if (a.partials) block_reduce_to_partials<D, 4>(st, a.partials + (int64_t)blockIdx.x * 4 * D, red);
+  if (stats) {   // fixed-order sum over the block's warps -> one partial row
+    __syncthreads();
+    float* out_row = a.partials + (int64_t)blockIdx.x * 4 * D;
+    for (int i = threadIdx.x; i < 4 * D; i += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarpsPerBlock; ++w) t += sacc[w * 4 * D + i];
+      out_row[i] = t;
+    }
+  }
 }
 
 // =============================================================================================
@@ -610,7 +634,10 @@ int alignn_b200_egc_forward(const alignn_b200_egc_fwd_args* a) {
   if (a->M && (!a->XP || !a->S || !a->H)) return ALIGNN_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)a->stream;
   const int grid = grid_for_rows(a->Nn);
-  DISPATCH_D(a->d, alignn::egc_forward_kernel<D><<<grid, alignn::kThreads, 0, st>>>(*a));
+  DISPATCH_D(a->d, {
+    const size_t smem_bytes = (size_t)(4 + (a->partials ? alignn::kWarpsPerBlock * 4 : 0)) * D * sizeof(float);
+    alignn::egc_forward_kernel<D><<<grid, alignn::kThreads, smem_bytes, st>>>(*a);   // <= 36 KB: no opt-in needed
+  });
   return check_launch();
 }
 
