@@ -113,7 +113,10 @@ class Graph:
             raise ValueError("batch_num_nodes / batch_num_edges do not add up")
         self.ndata: dict = {}
         self.edata: dict = {}
-        self._seg = None  # cached per-graph node offsets on device (for pooling)
+        # per-graph node offsets [B+1] (int32) for pooling; part of the structure that moves with .to()
+        seg = torch.zeros(self._bnn.numel() + 1, dtype=torch.int32)
+        seg[1:] = torch.cumsum(self._bnn, 0).to(torch.int32)
+        self._seg = seg
 
     # ---- DGLGraph API subset -----------------------------
     def edges(self):
@@ -156,19 +159,21 @@ class Graph:
             return self
         g = Graph(batch_num_nodes=self._bnn, batch_num_edges=self._bne,
                   _index=self.index.to(device, non_blocking))
+        g._seg = self._seg.to(device, non_blocking=non_blocking)
         g.ndata = {k: v.to(device, non_blocking=non_blocking) for k, v in self.ndata.items()}
         g.edata = {k: v.to(device, non_blocking=non_blocking) for k, v in self.edata.items()}
         return g
 
     def pin_memory(self) -> "Graph":
         g = Graph(batch_num_nodes=self._bnn, batch_num_edges=self._bne, _index=self.index.pin_memory())
+        g._seg = self._seg.pin_memory()
         g.ndata = {k: v.pin_memory() for k, v in self.ndata.items()}
         g.edata = {k: v.pin_memory() for k, v in self.edata.items()}
         return g
 
     def nbytes(self) -> int:
         """Bytes moved by `.to(device)` (structure + features)."""
-        n = self.index.nbytes()
+        n = self.index.nbytes() + self._seg.numel() * 4
         for d in (self.ndata, self.edata):
             n += sum(v.numel() * v.element_size() for v in d.values())
         return n
@@ -179,10 +184,8 @@ class Graph:
 
     def node_graph_offsets(self) -> torch.Tensor:
         """int32 [B+1] prefix of batch_num_nodes on this graph's device (per-graph pooling)."""
-        if self._seg is None or self._seg.device != self.device:
-            off = torch.zeros(self.batch_size + 1, dtype=torch.int32)
-            off[1:] = torch.cumsum(self._bnn, 0).to(torch.int32)
-            self._seg = off.to(self.device)
+        if self._seg.device != self.device:       # graph assembled directly from device tensors
+            self._seg = self._seg.to(self.device)
         return self._seg
 
     def line_graph(self, backtracking: bool = True, shared: bool = False) -> "Graph":
