@@ -68,15 +68,16 @@ _SIGNATURES = {
     "alignn_b200_affine_silu_residual": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, _fp]),
     "alignn_b200_egc_backward": (C.c_int, [C.POINTER(EgcBwdArgs)]),
     "alignn_b200_bn_backward_reduce": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, _fp, C.c_int, _fp]),
+    "alignn_b200_colsum_partials": (C.c_int, [_fp, C.c_int64, C.c_int, _fp, C.c_int, _fp]),
     "alignn_b200_colsum": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_int64, C.c_float, _fp, _fp]),
     "alignn_b200_gather_segment_sum": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int64, C.c_int, _fp, _fp, _fp]),
     "alignn_b200_gemm_weight_image_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "alignn_b200_gemm_prepare_weights": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int64, C.c_int, _fp, _fp]),
     "alignn_b200_gemm_nt": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, C.c_int, C.c_int, _fp, _fp, C.c_int64, _fp,
                                       C.c_int64, _fp]),
-    "alignn_b200_wgrad_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
-    "alignn_b200_wgrad": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, C.c_int64, C.c_int, C.c_int, _fp, C.c_int64, _fp,
-                                    C.c_size_t, _fp]),
+    "alignn_b200_wgrad_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int, C.c_int]),
+    "alignn_b200_wgrad": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _fp, C.c_int64,
+                                    _fp, C.c_size_t, _fp]),
     "alignn_b200_segment_mean": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, _fp, _fp]),
     "alignn_b200_segment_mean_backward": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, _fp, _fp]),
 }

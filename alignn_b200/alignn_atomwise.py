@@ -18,7 +18,8 @@ class MLPLayer(nn.Module):
         self.layer = nn.Sequential(nn.Linear(in_features, out_features), nn.LayerNorm(out_features), nn.SiLU())
 
     def forward(self, x):
-        return self.layer(x)
+        from .alignn import mlp_forward
+        return mlp_forward(self.layer, x)
 
 
 class EdgeGatedGraphConv(EdgeGatedGraphConvBase):
@@ -32,3 +33,165 @@ class ALIGNNConv(ALIGNNConvBase):
     """alignn/models/alignn_atomwise.py:211-246."""
 
     conv_cls = EdgeGatedGraphConv
+
+
+# --------------------------------------------------------------------------------------------------
+# ALIGNN-FF shell (energy + per-atom forces) on the same conv stack
+# --------------------------------------------------------------------------------------------------
+from typing import Literal  # noqa: E402
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from pydantic_settings import BaseSettings, SettingsConfigDict  # noqa: E402
+
+from . import ops  # noqa: E402
+from .alignn import RBFExpansion  # noqa: E402
+from .graph import as_graph, bond_cosines  # noqa: E402
+
+
+class ALIGNNAtomWiseConfig(BaseSettings):
+    """Field-for-field the reference schema (alignn/models/alignn_atomwise.py:28-79)."""
+
+    model_config = SettingsConfigDict(env_prefix="jv_model", extra="forbid")
+
+    name: Literal["alignn_atomwise"]
+    alignn_layers: int = 2
+    gcn_layers: int = 2
+    atom_input_features: int = 1
+    edge_input_features: int = 80
+    triplet_input_features: int = 40
+    embedding_features: int = 64
+    hidden_features: int = 64
+    output_features: int = 1
+    grad_multiplier: int = -1
+    calculate_gradient: bool = True
+    atomwise_output_features: int = 0
+    graphwise_weight: float = 1.0
+    gradwise_weight: float = 1.0
+    stresswise_weight: float = 0.0
+    atomwise_weight: float = 0.0
+    link: Literal["identity", "log", "logit"] = "identity"
+    zero_inflated: bool = False
+    classification: bool = False
+    force_mult_natoms: bool = False
+    energy_mult_natoms: bool = True
+    include_pos_deriv: bool = False
+    use_cutoff_function: bool = False
+    inner_cutoff: float = 3
+    stress_multiplier: float = 1
+    add_reverse_forces: bool = True
+    lg_on_fly: bool = True
+    batch_stress: bool = True
+    multiply_cutoff: bool = False
+    use_penalty: bool = True
+    extra_features: int = 0
+    exponent: int = 5
+    penalty_factor: float = 0.1
+    penalty_threshold: float = 1
+    additional_output_features: int = 0
+    additional_output_weight: float = 0
+
+
+class ALIGNNAtomWise(nn.Module):
+    """Energy (+ forces by autograd through the CUDA conv stack) -- the inference path of ALIGNN-FF
+    (alignn/models/alignn_atomwise.py:249-660, BASELINE config 4).
+
+    Same constructor/`forward((g, lg, lat))`/result-dict surface and state_dict names as the reference.
+    Forces use first-order autograd only (`create_graph=False`): the conv's autograd Function is
+    once-differentiable, so FF *training* on forces (double backward, :536) is not available.
+    Not built yet: stress (:567-638), include_pos_deriv, cutoff-function variants.
+    """
+
+    def __init__(self, config: ALIGNNAtomWiseConfig = ALIGNNAtomWiseConfig(name="alignn_atomwise")):
+        super().__init__()
+        c = self.config = config
+        for flag, why in ((c.include_pos_deriv, "include_pos_deriv"), (c.use_cutoff_function, "use_cutoff_function"),
+                          (c.stresswise_weight != 0, "stresswise_weight != 0"), (c.extra_features != 0, "extra_features")):
+            if flag:
+                raise NotImplementedError(f"alignn_b200.ALIGNNAtomWise: {why} is outside the built hot path")
+        self.classification = c.classification
+        self.atom_embedding = MLPLayer(c.atom_input_features, c.hidden_features)
+        self.edge_embedding = nn.Sequential(RBFExpansion(vmin=0, vmax=8.0, bins=c.edge_input_features),
+                                            MLPLayer(c.edge_input_features, c.embedding_features),
+                                            MLPLayer(c.embedding_features, c.hidden_features))
+        self.angle_embedding = nn.Sequential(RBFExpansion(vmin=-1, vmax=1.0, bins=c.triplet_input_features),
+                                             MLPLayer(c.triplet_input_features, c.embedding_features),
+                                             MLPLayer(c.embedding_features, c.hidden_features))
+        self.alignn_layers = nn.ModuleList([ALIGNNConv(c.hidden_features, c.hidden_features) for _ in range(c.alignn_layers)])
+        self.gcn_layers = nn.ModuleList([EdgeGatedGraphConv(c.hidden_features, c.hidden_features) for _ in range(c.gcn_layers)])
+        if c.atomwise_output_features > 0:
+            self.fc_atomwise = nn.Linear(c.hidden_features, c.atomwise_output_features)
+        if c.additional_output_features:
+            self.fc_additional_output = nn.Linear(c.hidden_features, c.additional_output_features)
+        if self.classification:
+            self.fc = nn.Linear(c.hidden_features, 1)
+            self.softmax = nn.Sigmoid()
+        else:
+            self.fc = nn.Linear(c.hidden_features, c.output_features)
+        if c.link == "log":
+            self.fc.bias.data = torch.tensor(np.log(0.7), dtype=torch.float)
+
+    def forward(self, g):
+        c = self.config
+        if len(self.alignn_layers) > 0:
+            if len(g) != 3:
+                raise NotImplementedError("pass (g, lg, lat); building L(g) inside forward is not part of the built path")
+            g, lg, lat = g
+            lg = as_graph(lg)
+        else:
+            g, lat = g[0], g[-1]
+            lg = None
+        g = as_graph(g)
+        result = {}
+        x = self.atom_embedding(g.ndata["atom_features"])
+        r = g.edata["r"]
+        if c.calculate_gradient:
+            r = r.detach().requires_grad_(True)                    # alignn_atomwise.py:416-420 (without mutating g)
+        bondlength = torch.norm(r, dim=1)
+        z = None
+        if lg is not None:
+            # lg_on_fly (:424-431): cosines recomputed from r so that the three-body terms are in the autograd graph
+            h = bond_cosines(r, lg) if (c.lg_on_fly or c.calculate_gradient) else lg.edata["h"]
+            z = self.angle_embedding(h)
+        y = self.edge_embedding(bondlength)
+        n_al, n_gcn = len(self.alignn_layers), len(self.gcn_layers)
+        for i, layer in enumerate(self.alignn_layers):
+            x, y, z = layer(g, lg, x, y, z, _need_z_out=(i + 1 < n_al))
+        for i, layer in enumerate(self.gcn_layers):
+            x, y = layer(g, x, y, _need_edge_out=(i + 1 < n_gcn))
+        hpool = ops.segment_mean(x, g.node_graph_offsets())
+        out = torch.squeeze(self.fc(hpool))
+        additional = torch.empty(1)
+        if c.additional_output_features > 0:
+            additional = self.fc_additional_output(hpool)
+        atomwise_pred = torch.empty(1)
+        if c.atomwise_output_features > 0 and c.atomwise_weight != 0:
+            atomwise_pred = self.fc_atomwise(x)
+        forces = torch.empty(1)
+        natoms = g.batch_num_nodes().to(out.device).to(out.dtype)
+        en_out = out * natoms if c.energy_mult_natoms else out + 0.0   # (:495-497; no aliasing of `out`, cf. App. D-12)
+        if c.use_penalty:                                               # (:498-510) zero for bonds >= threshold
+            pen = torch.where(bondlength < c.penalty_threshold, c.penalty_factor * (c.penalty_threshold - bondlength),
+                              torch.zeros_like(bondlength))
+            en_out = en_out + pen.sum()
+        if c.calculate_gradient:
+            (dr,) = torch.autograd.grad(en_out, r, grad_outputs=torch.ones_like(en_out),
+                                        create_graph=False, retain_graph=self.training)
+            pair_forces = c.grad_multiplier * dr                         # (:530-539)
+            if c.force_mult_natoms:
+                pair_forces = pair_forces * g.num_nodes()
+            src, dst = g.index.src.long(), g.index.dst.long()
+            zeros = torch.zeros(g.num_nodes(), 3, device=r.device, dtype=r.dtype)
+            forces = zeros.index_add(0, dst, pair_forces)                # copy_e/sum over in-edges (:547-550)
+            if c.add_reverse_forces:
+                forces = forces - zeros.index_add(0, src, pair_forces)   # ... minus over out-edges (:555-563)
+            forces = torch.squeeze(forces)
+            result["pair_forces"] = pair_forces
+        if c.link == "log":
+            out = torch.exp(out)
+        elif c.link == "logit":
+            out = torch.sigmoid(out)
+        if self.classification:
+            out = self.softmax(out)
+        result.update(out=out, additional=additional, grad=forces, stresses=torch.empty(1), atomwise_pred=atomwise_pred)
+        return result

@@ -458,6 +458,27 @@ bn_backward_reduce_kernel(const float* __restrict__ R, const float* __restrict__
   block_reduce_to_partials<D, 2>(acc, partials + (int64_t)blockIdx.x * 2 * D, red);
 }
 
+// per-block partial column sums of a tall [n, D] matrix (bias gradients of the embedding Linears)
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+colsum_partials_kernel(const float* __restrict__ a, int64_t n, float* __restrict__ partials) {
+  constexpr int V = RowCfg<D>::VPL;
+  __shared__ float red[kWarpsPerBlock * D];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  float acc[1][V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[0][k] = 0.f;
+  for (int64_t r = warp0; r < n; r += nwarps) {
+    float v[V];
+    ld_row<D, false>(v, a + r * D, lane);
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[0][k] += v[k];
+  }
+  block_reduce_to_partials<D, 1>(acc, partials + (int64_t)blockIdx.x * D, red);
+}
+
 // out[c] = alpha * sum_r a[r*stride + c]; 32 columns per block x 8 row lanes, fp64, fixed order.
 // Used on per-block partial buffers (rows <= kMaxBlocks).
 __global__ void __launch_bounds__(256)
@@ -718,6 +739,15 @@ int alignn_b200_bn_backward_reduce(const float* R, const float* g_out, const flo
   if (partial_rows < grid) return ALIGNN_ERR_WORKSPACE;
   DISPATCH_D(d, alignn::bn_backward_reduce_kernel<D><<<grid, alignn::kThreads, 0, (cudaStream_t)stream>>>(
                     R, g_out, scale, shift, mean, rstd, n, partials));
+  return check_launch();
+}
+
+int alignn_b200_colsum_partials(const float* a, int64_t n, int d, float* partials, int partial_rows, alignn_stream_t stream) {
+  if (!supported_d(d)) return ALIGNN_ERR_UNSUPPORTED_D;
+  if (n <= 0 || !a || !partials) return ALIGNN_ERR_BAD_ARG;
+  const int grid = grid_for_rows(n);
+  if (partial_rows < grid) return ALIGNN_ERR_WORKSPACE;
+  DISPATCH_D(d, alignn::colsum_partials_kernel<D><<<grid, alignn::kThreads, 0, (cudaStream_t)stream>>>(a, n, partials));
   return check_launch();
 }
 

@@ -1,5 +1,5 @@
-// Weight gradients of the Linear layers: C[g][o][i] = sum_r A[r, g*D + o] * B[r, i], r over the rows
-// (edges or nodes) of the batch -- a D x D output with a very long reduction (K = 276 480 rows for the
+// Weight gradients of the Linear layers: C[g][o][i] = sum_r A[r, g*DA + o] * B[r, i], r over the rows
+// (edges or nodes) of the batch -- a DA x DB output with a very long reduction (K = 276 480 rows for the
 // edge gate on L(g)).  Tensor cores via tcgen05.mma kind::f16, bf16x3 split (tc_common.cuh).
 //
 // Both operands are "MN-major" for this product (the contraction index is the ROW of the row-major
@@ -26,26 +26,36 @@ constexpr int THREADS = LOADERS + 32;
 constexpr uint32_t SBO = 128;
 constexpr int kNumSMsWgrad = 148;
 
-template <int D>
+template <int DA, int DB>   // A: [K, groups*DA] (output-gradient side), B: [K, DB] (input side); out tile DA x DB
 struct Cfg {
-  static constexpr int MT = (D + 127) / 128;          // number of M=128 UMMA tiles
+  static constexpr int MT = (DA + 127) / 128;         // number of M=128 UMMA tiles
   static constexpr int A_ROWS = MT * 128;             // padded channel count of the A plane
   static constexpr int A_PLANE = A_ROWS * BK * 2;
-  static constexpr int B_PLANE = D * BK * 2;
+  static constexpr int B_PLANE = DB * BK * 2;
   static constexpr uint32_t LBO_A = (A_ROWS / 8) * 128;
-  static constexpr uint32_t LBO_B = (D / 8) * 128;
+  static constexpr uint32_t LBO_B = (DB / 8) * 128;
   static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
   static constexpr int PIPE = STAGES * STAGE;
   static constexpr int SMEM = PIPE + 128;
-  static constexpr int TMEM_COLS = (MT * D) < 32 ? 32 : (MT * D);     // 32, 64, 128, 512
-  static constexpr int TASKS = 2 * 4 * (D / 16);      // (matrix, 8-row group, 16-channel group) per stage
+  static constexpr int ACC_COLS = MT * DB;
+  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
+  static constexpr int TASKS_A = 4 * (DA / 16);       // (8-row group, 16-channel group) tasks per stage
+  static constexpr int TASKS = TASKS_A + 4 * (DB / 16);
 };
 
-template <int D>
+// task -> (matrix, 8-row group, 16-channel group); all divisors are compile-time constants (shifts / mul-shift)
+template <int DA, int DB>
+__device__ __forceinline__ void decode_task(int task, int& mat, int& eg, int& og) {
+  constexpr int TA = 4 * (DA / 16);
+  if (task < TA) { mat = 0; eg = task / (DA / 16); og = task % (DA / 16); }
+  else { const int rem = task - TA; mat = 1; eg = rem / (DB / 16); og = rem % (DB / 16); }
+}
+
+template <int DA, int DB>
 __global__ void __launch_bounds__(THREADS, 1)
 wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int64_t K,
                     int rows_per_cta, float* __restrict__ partials) {
-  using F = Cfg<D>;
+  using F = Cfg<DA, DB>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + F::PIPE);
   uint64_t* empty = full + STAGES;
@@ -57,14 +67,14 @@ wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __res
   const int64_t r_begin = (int64_t)cta * rows_per_cta;
   const int64_t r_end = (r_begin + rows_per_cta < K) ? r_begin + rows_per_cta : K;
   const int nk = r_end > r_begin ? (int)((r_end - r_begin + BK - 1) / BK) : 0;
-  const float* Ag = A + (int64_t)group * D;
+  const float* Ag = A + (int64_t)group * DA;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], LOAD_WARPS); tc::mbar_init(&empty[s], 1); }
     tc::mbar_init(accbar, 1);
     tc::mbar_fence_init();
   }
-  if (D < 128) {   // padded A rows [D, 128) are never written by the loaders: zero the planes once
+  if (DA < 128) {   // padded A rows [DA, 128) are never written by the loaders: zero the planes once
     for (int i = tid; i < F::PIPE / 16; i += THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   }
   if (warp == LOAD_WARPS) tc::tmem_alloc(tmem_slot, F::TMEM_COLS);
@@ -76,7 +86,7 @@ wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __res
 
   if (warp < LOAD_WARPS) {
     // ================= loader / converter =================
-    constexpr int TPW = F::TASKS / LOAD_WARPS;          // tasks per warp per stage (>= 1 for D >= 32... see launch)
+    constexpr int TPW = (F::TASKS + LOAD_WARPS - 1) / LOAD_WARPS;   // tasks per warp per stage
     // half-warp = 8 contraction rows x 2 adjacent float4 -> one 128-byte core matrix: conflict-free 64-bit stores
     const int e_l = (lane >> 1) & 7, oq = (lane >> 4) * 2 + (lane & 1);
     constexpr int NT = TPW > 0 ? TPW : 1;
@@ -85,8 +95,8 @@ wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __res
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
         const int task = warp * NT + t;
-        const int mat = task / (4 * (D / 16)), rem = task % (4 * (D / 16));
-        const int eg = rem / (D / 16), og = rem % (D / 16);
+        int mat, eg, og;
+        decode_task<DA, DB>(task, mat, eg, og);
         const int64_t r = r0 + eg * 8 + e_l;
         const float* src = mat == 0 ? Ag + r * lda : B + r * ldb;
         v[t] = (task < F::TASKS && r < r_end) ? __ldcs(reinterpret_cast<const float4*>(src + (og * 4 + oq) * 4))
@@ -101,8 +111,8 @@ wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __res
       for (int t = 0; t < NT; ++t) {
         const int task = warp * NT + t;
         if (task < F::TASKS) {
-          const int mat = task / (4 * (D / 16)), rem = task % (4 * (D / 16));
-          const int eg = rem / (D / 16), og = rem % (D / 16);
+          int mat, eg, og;
+          decode_task<DA, DB>(task, mat, eg, og);
           const int o4 = og * 4 + oq, edge = eg * 8 + e_l;
           uint2 hi, lo;
           tc::split4(v[t], hi, lo);
@@ -132,33 +142,33 @@ wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __res
     // ================= epilogue: TMEM -> partial tile in global =================
     tc::mbar_wait(accbar, 0);
     tc::fence_after_sync();
-    float* out = partials + ((int64_t)group * gridDim.x + cta) * D * D;
+    float* out = partials + ((int64_t)group * gridDim.x + cta) * DA * DB;
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int row_in_tile = q * 32 + lane;
-    // D = 256: warps 0-3 read M tile 0, warps 4-7 M tile 1.  D = 128: the two warp quads split the
-    // columns.  D <= 64: warps 0-3 read everything.
+    // DA = 256: warps 0-3 read M tile 0, warps 4-7 M tile 1.  One M tile and DB >= 128: the two warp quads
+    // split the columns.  Otherwise warps 0-3 read everything.
     const int mt = (F::MT == 2) ? (warp >> 2) : 0;
-    const bool halves = (F::MT == 1) && (D >= 128);
-    const int c_begin = halves ? (warp >> 2) * (D / 2) : 0;
-    const int c_end = (F::MT == 2) ? D : (halves ? c_begin + D / 2 : ((warp >> 2) == 0 ? D : 0));
+    const bool halves = (F::MT == 1) && (DB >= 128);
+    const int c_begin = halves ? (warp >> 2) * (DB / 2) : 0;
+    const int c_end = (F::MT == 2) ? DB : (halves ? c_begin + DB / 2 : ((warp >> 2) == 0 ? DB : 0));
     const int o = mt * 128 + row_in_tile;
     if (nk > 0) {
       for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         float v[32];
-        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * D + c0), v);
-        if (o < D) {
+        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * DB + c0), v);
+        if (o < DA) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(out + (int64_t)o * D + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            *reinterpret_cast<float4*>(out + (int64_t)o * DB + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
       }
-    } else if (o < D) {
+    } else if (o < DA) {
       for (int c0 = c_begin; c0 < c_end; c0 += 4)
-        *reinterpret_cast<float4*>(out + (int64_t)o * D + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(out + (int64_t)o * DB + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   } else if (lane == 0) {
     // ================= MMA issuer =================
-    constexpr uint32_t IDESC = tc::idesc_bf16_f32(128, D) | (1u << 15) | (1u << 16);   // A and B MN-major
+    constexpr uint32_t IDESC = tc::idesc_bf16_f32(128, DB) | (1u << 15) | (1u << 16);   // A and B MN-major
     for (int kc = 0; kc < nk; ++kc) {
       const int s = kc % STAGES;
       tc::mbar_wait(&full[s], (kc / STAGES) & 1);
@@ -173,7 +183,7 @@ wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __res
           const uint32_t ao = j * 2 * F::LBO_A + mt * 16 * SBO;
           const uint64_t a_hi = tc::smem_desc(base + ao, F::LBO_A, SBO);
           const uint64_t a_lo = tc::smem_desc(base + F::A_PLANE + ao, F::LBO_A, SBO);
-          const uint32_t d = tmem + (uint32_t)(mt * D);
+          const uint32_t d = tmem + (uint32_t)(mt * DB);
           tc::mma_bf16_ss(d, a_lo, b_hi, IDESC, (kc | j) != 0);
           tc::mma_bf16_ss(d, a_hi, b_lo, IDESC, 1);
           tc::mma_bf16_ss(d, a_hi, b_hi, IDESC, 1);
@@ -188,9 +198,9 @@ wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __res
   if (warp == LOAD_WARPS) tc::tmem_dealloc(tmem, F::TMEM_COLS);
 }
 
-// out[g][o][i] = sum_c partials[g][c][o][i]  (fixed order)
+// out[g*DA + o][i] = sum_c partials[g][c][o][i]  (fixed order)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partials, int ctas, int64_t tile, float* __restrict__ out,
-                                    int64_t ld_out, int D) {
+                                    int64_t ld_out, int DA, int DB) {
   const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int g = blockIdx.y;
   if (idx >= tile) return;
@@ -200,8 +210,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partials, int ctas
     const float4 v = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)c * tile));
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
-  const int64_t o = idx / D, i = idx % D;
-  *reinterpret_cast<float4*>(out + ((int64_t)g * D + o) * ld_out + i) = s;
+  const int64_t o = idx / DB, i = idx % DB;
+  *reinterpret_cast<float4*>(out + ((int64_t)g * DA + o) * ld_out + i) = s;
 }
 
 inline int ctas_for(int64_t K, int groups) {
@@ -213,25 +223,31 @@ inline int ctas_for(int64_t K, int groups) {
   return per_group;
 }
 
-template <int D>
+template <int DA, int DB>
 int launch(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int groups, float* out, int64_t ld_out,
            float* ws, cudaStream_t st) {
-  using F = Cfg<D>;
+  using F = Cfg<DA, DB>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_bf16x3_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_bf16x3_kernel<DA, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
     if (e != cudaSuccess) return record_cuda_error((int)e);
     configured = true;
   }
   const int ctas = ctas_for(K, groups);
   int64_t rows = (K + ctas - 1) / ctas;
   rows = (rows + BK - 1) / BK * BK;               // slabs start on a stage boundary
-  wgrad_bf16x3_kernel<D><<<dim3(ctas, groups), THREADS, F::SMEM, st>>>(A, lda, B, ldb, K, (int)rows, ws);
+  wgrad_bf16x3_kernel<DA, DB><<<dim3(ctas, groups), THREADS, F::SMEM, st>>>(A, lda, B, ldb, K, (int)rows, ws);
   int rc = check_launch();
   if (rc != ALIGNN_OK) return rc;
-  const int64_t tile = (int64_t)D * D;
-  wgrad_reduce_kernel<<<dim3((unsigned)((tile / 4 + 255) / 256), groups), 256, 0, st>>>(ws, ctas, tile, out, ld_out, D);
+  const int64_t tile = (int64_t)DA * DB;
+  wgrad_reduce_kernel<<<dim3((unsigned)((tile / 4 + 255) / 256), groups), 256, 0, st>>>(ws, ctas, tile, out, ld_out, DA, DB);
   return check_launch();
+}
+
+// supported (DA, DB): square conv shapes and the embedding-MLP shapes (inputs zero-padded to a multiple of 32)
+inline bool shape_ok(int DA, int DB) {
+  if (DA == DB) return DA == 32 || DA == 64 || DA == 128 || DA == 256;
+  return (DA == 256 && (DB == 64 || DB == 96)) || (DA == 64 && (DB == 96 || DB == 32)) || (DA == 32 && DB == 64);
 }
 
 }  // namespace wgrad
@@ -239,27 +255,26 @@ int launch(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, 
 
 extern "C" {
 
-size_t alignn_b200_wgrad_workspace_bytes(int64_t K, int D, int groups) {
-  if (K < 0 || groups < 1 || (D != 32 && D != 64 && D != 128 && D != 256)) return 0;
-  return (size_t)alignn::wgrad::ctas_for(K, groups) * groups * D * D * sizeof(float);
+size_t alignn_b200_wgrad_workspace_bytes(int64_t K, int DA, int DB, int groups) {
+  if (K < 0 || groups < 1 || !alignn::wgrad::shape_ok(DA, DB)) return 0;
+  return (size_t)alignn::wgrad::ctas_for(K, groups) * groups * DA * DB * sizeof(float);
 }
 
-int alignn_b200_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int D, int groups, float* out,
-                      int64_t ld_out, void* workspace, size_t workspace_bytes, alignn_stream_t stream) {
+int alignn_b200_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int DA, int DB, int groups,
+                      float* out, int64_t ld_out, void* workspace, size_t workspace_bytes, alignn_stream_t stream) {
   using namespace alignn::wgrad;
-  if (K < 0 || groups < 1 || !out || ld_out < D || (ld_out % 4)) return ALIGNN_ERR_BAD_ARG;
-  if (D != 32 && D != 64 && D != 128 && D != 256) return ALIGNN_ERR_UNSUPPORTED_D;
-  if (K > 0 && (!A || !B || lda < (int64_t)groups * D || ldb < D || (lda % 4) || (ldb % 4))) return ALIGNN_ERR_BAD_ARG;
+  if (K < 0 || groups < 1 || !out || ld_out < DB || (ld_out % 4)) return ALIGNN_ERR_BAD_ARG;
+  if (!shape_ok(DA, DB)) return ALIGNN_ERR_UNSUPPORTED_D;
+  if (K > 0 && (!A || !B || lda < (int64_t)groups * DA || ldb < DB || (lda % 4) || (ldb % 4))) return ALIGNN_ERR_BAD_ARG;
   if (K >= ((int64_t)1 << 31) * BK) return ALIGNN_ERR_BAD_ARG;
-  if (!workspace || workspace_bytes < alignn_b200_wgrad_workspace_bytes(K, D, groups)) return ALIGNN_ERR_WORKSPACE;
+  if (!workspace || workspace_bytes < alignn_b200_wgrad_workspace_bytes(K, DA, DB, groups)) return ALIGNN_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = reinterpret_cast<float*>(workspace);
-  switch (D) {
-    case 256: return launch<256>(A, lda, B, ldb, K, groups, out, ld_out, ws, st);
-    case 128: return launch<128>(A, lda, B, ldb, K, groups, out, ld_out, ws, st);
-    case 64: return launch<64>(A, lda, B, ldb, K, groups, out, ld_out, ws, st);
-    default: return launch<32>(A, lda, B, ldb, K, groups, out, ld_out, ws, st);
-  }
+#define WG(a, b) if (DA == a && DB == b) return launch<a, b>(A, lda, B, ldb, K, groups, out, ld_out, ws, st)
+  WG(256, 256); WG(128, 128); WG(64, 64); WG(32, 32);
+  WG(256, 64); WG(256, 96); WG(64, 96); WG(64, 32); WG(32, 64);
+#undef WG
+  return ALIGNN_ERR_UNSUPPORTED_D;
 }
 
 }  // extern "C"

@@ -257,17 +257,74 @@ def gemm_nt(A: torch.Tensor, w: WeightImage, bias: Optional[torch.Tensor] = None
     return out
 
 
+def wgrad_supported(DA: int, DB: int) -> bool:
+    return int(_lib.load().alignn_b200_wgrad_workspace_bytes(32, DA, DB, 1)) > 0
+
+
 def wgrad(A: torch.Tensor, B: torch.Tensor, groups: int = 1) -> torch.Tensor:
-    """out[g*D + o, i] = sum_r A[r, g*D + o] * B[r, i]  (dL/dW of a Linear: A = output grads, B = inputs)."""
+    """out[g*DA + o, i] = sum_r A[r, g*DA + o] * B[r, i]  (dL/dW of a Linear: A = output grads, B = inputs)."""
     lib = _lib.load()
     require_cuda(A, B)
-    K, D = B.shape
-    if A.shape != (K, groups * D):
-        raise RuntimeError(f"wgrad: A must be [{K},{groups * D}], got {tuple(A.shape)}")
-    _check_d(D)
-    out = torch.empty(groups * D, D, device=A.device, dtype=torch.float32)
-    nbytes = int(lib.alignn_b200_wgrad_workspace_bytes(K, D, groups))
+    K, DB = B.shape
+    if A.dim() != 2 or A.shape[0] != K or A.shape[1] % groups:
+        raise RuntimeError(f"wgrad: A must be [{K}, groups*DA], got {tuple(A.shape)}")
+    DA = A.shape[1] // groups
+    nbytes = int(lib.alignn_b200_wgrad_workspace_bytes(K, DA, DB, groups))
+    if nbytes == 0 and K >= 0:
+        raise RuntimeError(f"alignn_b200 wgrad: unsupported shape DA={DA}, DB={DB}")
+    out = torch.empty(groups * DA, DB, device=A.device, dtype=torch.float32)
     ws = torch.empty(max(nbytes, 16), device=A.device, dtype=torch.uint8)
-    _lib.check(lib.alignn_b200_wgrad(ptr(A), A.stride(0), ptr(B), B.stride(0), K, D, groups, ptr(out), D, ptr_any(ws), nbytes,
-                                      stream_ptr()), "alignn_b200_wgrad")
+    _lib.check(lib.alignn_b200_wgrad(ptr(A), A.stride(0), ptr(B), B.stride(0), K, DA, DB, groups, ptr(out), DB, ptr_any(ws),
+                                      nbytes, stream_ptr()), "alignn_b200_wgrad")
     return out
+
+
+def colsum_rows(a: torch.Tensor) -> torch.Tensor:
+    """Column sums of a tall contiguous [n, d] matrix, deterministic two-stage reduction."""
+    lib = _lib.load()
+    require_cuda(a)
+    n, d = a.shape
+    _check_d(d)
+    rows = partial_rows(n, d)
+    part = torch.empty(rows, d, device=a.device, dtype=torch.float32)
+    _lib.check(lib.alignn_b200_colsum_partials(ptr(a), n, d, ptr(part), rows, stream_ptr()), "alignn_b200_colsum_partials")
+    return colsum(part)
+
+
+class _TCLinearFn(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 bf16x3 GEMMs (forward, data gradient, weight gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, k_pad):
+        x = x.contiguous()
+        if k_pad != x.shape[1]:
+            x = torch.nn.functional.pad(x, (0, k_pad - x.shape[1]))
+            w = torch.nn.functional.pad(weight, (0, k_pad - weight.shape[1]))
+        else:
+            w = weight.contiguous()
+        ctx.save_for_backward(x, w)
+        ctx.k_in = weight.shape[1]
+        return gemm_nt(x, WeightImage(w), bias.contiguous())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, go):
+        x, w = ctx.saved_tensors
+        go = go.contiguous()
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm_nt(go, WeightImage(w, transpose=True))[:, :ctx.k_in]
+        gw = wgrad(go, x, 1)[:, :ctx.k_in]
+        gb = colsum_rows(go)
+        return gx, gw, gb, None
+
+
+def tc_linear_supported(in_features: int, out_features: int) -> bool:
+    k_pad = (in_features + 31) // 32 * 32
+    return out_features in _lib.SUPPORTED_D and wgrad_supported(out_features, k_pad)
+
+
+def tc_linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """nn.Linear forward/backward on the tensor-core kernels; the input width is zero-padded to a multiple of 32."""
+    k_pad = (weight.shape[1] + 31) // 32 * 32
+    return _TCLinearFn.apply(x, weight, bias, k_pad)

@@ -298,27 +298,43 @@ def run_ours(args):
     # ---- CUDA graphs: one per resident batch and one per host batch (H2D copies inside the graph) --------
     # The step is ~650 launches of which most are small (g-graph convs, norms, optimizer); replaying them as a
     # graph removes the host launch cost.  Shapes are static here; a real variable-size loader would bucket.
-    graphs_res, graphs_e2e, launches_per_step = [], [], None
+    # The gradient all-reduce stays OUTSIDE the graphs (an NCCL collective inside a captured graph hung on this
+    # stack): per step = replay(zero_grad + forward + backward) -> eager flat all-reduce -> replay(optimizer).
+    graphs_res, graphs_e2e, graph_opt, launches_per_step = [], [], None, None
+
+    def fwd_bwd(batch):
+        g, lg, lat, tgt = batch
+        reducer.zero_grad()
+        out = model((g, lg, lat))
+        loss = (out - tgt).abs().mean()
+        loss.backward()
+        return loss
+
     if use_graph:
         pool = None
         for b in range(nb):
             gr = torch.cuda.CUDAGraph()
             l0 = _lib.launch_count()
             with torch.cuda.graph(gr, pool=pool):
-                loss_b = step(resident[b])
+                loss_b = fwd_bwd(resident[b])
             launches_per_step = _lib.launch_count() - l0
             pool = pool or gr.pool()
             graphs_res.append((gr, loss_b))
         for b in range(nb):
             gr = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gr, pool=pool):
-                loss_b = step(h2d(b))
+                loss_b = fwd_bwd(h2d(b))
             graphs_e2e.append((gr, loss_b))
+        graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph_opt, pool=pool):
+            opt.step()
         barrier()
 
     def run_resident(i):
         if use_graph:
             graphs_res[i % nb][0].replay()
+            reducer.all_reduce()
+            graph_opt.replay()
         else:
             step(resident[i % nb])
 
@@ -326,6 +342,8 @@ def run_ours(args):
         if use_graph:
             gr, loss_b = graphs_e2e[i % nb]
             gr.replay()
+            reducer.all_reduce()
+            graph_opt.replay()
             return loss_b.item()                              # D2H + sync, as train.py:300-305 does
         return step(h2d(i)).item()
 

@@ -171,6 +171,10 @@ int alignn_b200_bn_backward_reduce(const float* R, const float* g_out, const flo
                                    const float* mean, const float* rstd, int64_t n, int d,
                                    float* partials, int partial_rows, alignn_stream_t stream);
 
+/* Per-block partial column sums of a tall contiguous [n, d] matrix (rows: alignn_b200_egc_partial_rows(n, d));
+ * finish with alignn_b200_colsum.  Used for the bias gradients of the embedding Linears (alignn.py:201-222). */
+int alignn_b200_colsum_partials(const float* a, int64_t n, int d, float* partials, int partial_rows, alignn_stream_t stream);
+
 /* Deterministic column sum of a [rows, cols] fp32 matrix with row stride `stride` floats into
  * out[cols] (fp64 accumulation), optionally scaled by `alpha`. */
 int alignn_b200_colsum(const float* a, int64_t rows, int cols, int64_t stride, float alpha, float* out,
@@ -201,12 +205,14 @@ int alignn_b200_gemm_nt(const float* A, int64_t lda, const void* w_image, int64_
                         const float* R, int64_t ldr, float* C, int64_t ldc, alignn_stream_t stream);
 
 /* Weight gradients on the tensor cores (split-K over the batch rows, deterministic two-stage sum):
- *     out[g*D + o, i] = sum_{r < K} A[r, g*D + o] * B[r, i]        g < groups,  o, i < D
- * i.e. dL/dW = GM^T y (groups = 1) and dL/dWcat = GP^T x (groups = 4) of SURVEY.md App. B.
- * `workspace` holds the per-CTA partial tiles (size from alignn_b200_wgrad_workspace_bytes). */
-size_t alignn_b200_wgrad_workspace_bytes(int64_t K, int D, int groups);
-int alignn_b200_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int D, int groups, float* out,
-                      int64_t ld_out, void* workspace, size_t workspace_bytes, alignn_stream_t stream);
+ *     out[g*DA + o, i] = sum_{r < K} A[r, g*DA + o] * B[r, i]        g < groups,  o < DA,  i < DB
+ * i.e. dL/dW = GM^T y (groups = 1) and dL/dWcat = GP^T x (groups = 4) of SURVEY.md App. B, and the
+ * rectangular weight gradients of the embedding MLPs (alignn.py:201-222).  Supported (DA, DB): DA == DB in
+ * {32, 64, 128, 256}; (256,64), (256,96), (64,96), (64,32), (32,64).
+ * `workspace` holds the per-CTA partial tiles (size from alignn_b200_wgrad_workspace_bytes; 0 = unsupported). */
+size_t alignn_b200_wgrad_workspace_bytes(int64_t K, int DA, int DB, int groups);
+int alignn_b200_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int DA, int DB, int groups,
+                      float* out, int64_t ld_out, void* workspace, size_t workspace_bytes, alignn_stream_t stream);
 
 /* Per-graph mean over node rows (dgl.nn.AvgPooling, alignn.py:325) and its backward. */
 int alignn_b200_segment_mean(const float* x, const int32_t* graph_ptr /*[B+1]*/, int64_t B, int d, float* out,

@@ -79,3 +79,16 @@ def test_wgrad_matches_fp64(K, D, groups):
     err = (out.double() - ref).abs().max().item()
     assert err <= 2e-5 * ref.abs().max().item(), (K, D, groups, err, ref.abs().max().item())
     assert torch.equal(out, ops.wgrad(A, B, groups))          # deterministic split-K
+
+
+@pytest.mark.parametrize("K,DA,DB", [(276480, 256, 64), (23040, 256, 96), (5000, 64, 96), (777, 64, 32), (777, 32, 64)])
+def test_wgrad_rectangular_matches_fp64(K, DA, DB):
+    """Embedding-MLP weight gradients: [out, in_padded] with out != in."""
+    g = torch.Generator(device="cpu").manual_seed(K + DA + DB)
+    A = torch.randn(K, DA, generator=g).to(DEV)
+    B = torch.randn(K, DB, generator=g).to(DEV)
+    out = ops.wgrad(A, B, 1)
+    ref = A.double().t() @ B.double()
+    assert out.shape == (DA, DB)
+    assert (out.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    assert not ops.wgrad_supported(48, 64)

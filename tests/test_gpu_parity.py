@@ -236,3 +236,23 @@ def test_launch_counter_counts_library_kernels():
     with torch.no_grad():
         conv(g.to(DEV), GI.features(1, g.num_nodes(), 64).to(DEV), GI.features(2, g.num_edges(), 64).to(DEV))
     assert _lib.launch_count() - before == 5      # 2 weight splits + 2 tensor-core GEMMs + 1 fused edge kernel
+
+
+def test_atomwise_energy_and_forces_vs_reference_golden(golden_dir):
+    """BASELINE config 4 path (ALIGNN-FF energy + forces by autograd through the conv stack) against the
+    unmodified reference's ALIGNNAtomWise outputs."""
+    from alignn_b200.alignn_atomwise import ALIGNNAtomWise, ALIGNNAtomWiseConfig
+    gold = np.load(os.path.join(golden_dir, "atomwise_small.npz"))
+    g, lg, lat, _ = synthetic.make_batch(batch_size=2, atoms=8, k=12, seed=41, vary_atoms=True)
+    m = ALIGNNAtomWise(ALIGNNAtomWiseConfig(name="alignn_atomwise", alignn_layers=2, gcn_layers=2, hidden_features=64,
+                                            embedding_features=32, atom_input_features=92))
+    GI.fill_state_dict(m, 400)
+    m.to(DEV).eval()
+    res = m((g.to(DEV), lg.to(DEV), lat.to(DEV)))
+    assert_close(res["out"], gold["out"], what="energy per atom")
+    assert_close(res["grad"], gold["forces"], what="forces")
+    assert_close(res["pair_forces"], gold["pair_forces"], what="pair forces")
+    # size-independent property (test_force_reduction.py:212-229): net force on every crystal is zero
+    off = g.node_graph_offsets().tolist()
+    for a, b in zip(off[:-1], off[1:]):
+        assert float(res["grad"][a:b].sum(0).abs().max()) < 1e-4
