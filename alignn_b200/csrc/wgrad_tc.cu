@@ -43,14 +43,6 @@ struct Cfg {
   static constexpr int TASKS = TASKS_A + 4 * (DB / 16);
 };
 
-// task -> (matrix, 8-row group, 16-channel group); all divisors are compile-time constants (shifts / mul-shift)
-template <int DA, int DB>
-__device__ __forceinline__ void decode_task(int task, int& mat, int& eg, int& og) {
-  constexpr int TA = 4 * (DA / 16);
-  if (task < TA) { mat = 0; eg = task / (DA / 16); og = task % (DA / 16); }
-  else { const int rem = task - TA; mat = 1; eg = rem / (DB / 16); og = rem % (DB / 16); }
-}
-
 template <int DA, int DB>
 __global__ void __launch_bounds__(THREADS, 1)
 wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int64_t K,
@@ -86,21 +78,31 @@ wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __res
 
   if (warp < LOAD_WARPS) {
     // ================= loader / converter =================
-    constexpr int TPW = (F::TASKS + LOAD_WARPS - 1) / LOAD_WARPS;   // tasks per warp per stage
+    // Work split with compile-time structure: slot (mat, eg, j) of warp w covers the 16-channel group
+    // og = w + 8*j of 8-row group eg of matrix mat -- only og depends on the warp, so no index math is left
+    // in the hot loop (a flat task id cost register spills and ~2x the time).
     // half-warp = 8 contraction rows x 2 adjacent float4 -> one 128-byte core matrix: conflict-free 64-bit stores
     const int e_l = (lane >> 1) & 7, oq = (lane >> 4) * 2 + (lane & 1);
-    constexpr int NT = TPW > 0 ? TPW : 1;
+    constexpr int JA = (DA / 16 + LOAD_WARPS - 1) / LOAD_WARPS, JB = (DB / 16 + LOAD_WARPS - 1) / LOAD_WARPS;
+    constexpr int NT = 4 * (JA + JB);
     auto load_chunk = [&](float4 (&v)[NT], int kc) {
-      const int64_t r0 = r_begin + (int64_t)kc * BK;
+      const int64_t r0 = r_begin + (int64_t)kc * BK + e_l;
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        const int task = warp * NT + t;
-        int mat, eg, og;
-        decode_task<DA, DB>(task, mat, eg, og);
-        const int64_t r = r0 + eg * 8 + e_l;
-        const float* src = mat == 0 ? Ag + r * lda : B + r * ldb;
-        v[t] = (task < F::TASKS && r < r_end) ? __ldcs(reinterpret_cast<const float4*>(src + (og * 4 + oq) * 4))
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int eg = 0; eg < 4; ++eg) {
+        const int64_t r = r0 + eg * 8;
+        const bool rv = r < r_end;
+#pragma unroll
+        for (int j = 0; j < JA; ++j) {
+          const int og = warp + LOAD_WARPS * j;
+          v[eg * (JA + JB) + j] = (rv && og < DA / 16) ? __ldcs(reinterpret_cast<const float4*>(Ag + r * lda + (og * 4 + oq) * 4))
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < JB; ++j) {
+          const int og = warp + LOAD_WARPS * j;
+          v[eg * (JA + JB) + JA + j] = (rv && og < DB / 16) ? __ldcs(reinterpret_cast<const float4*>(B + r * ldb + (og * 4 + oq) * 4))
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     };
     auto store_chunk = [&](const float4 (&v)[NT], int kc) {
@@ -108,20 +110,23 @@ wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __res
       if (kc >= STAGES) tc::mbar_wait(&empty[s], ((kc / STAGES) - 1) & 1);
       uint8_t* st = smem + s * F::STAGE;
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        const int task = warp * NT + t;
-        if (task < F::TASKS) {
-          int mat, eg, og;
-          decode_task<DA, DB>(task, mat, eg, og);
-          const int o4 = og * 4 + oq, edge = eg * 8 + e_l;
-          uint2 hi, lo;
-          tc::split4(v[t], hi, lo);
-          const uint32_t lbo = mat == 0 ? F::LBO_A : F::LBO_B;
-          const int plane = mat == 0 ? F::A_PLANE : F::B_PLANE;
-          uint8_t* base = st + (mat == 0 ? 0 : 2 * F::A_PLANE);
-          const int off = (o4 >> 1) * (int)SBO + (edge >> 3) * (int)lbo + (edge & 7) * 16 + (o4 & 1) * 8;
-          *reinterpret_cast<uint2*>(base + off) = hi;
-          *reinterpret_cast<uint2*>(base + plane + off) = lo;
+      for (int eg = 0; eg < 4; ++eg) {
+        const int edge = eg * 8 + e_l;
+#pragma unroll
+        for (int j = 0; j < JA + JB; ++j) {
+          const bool isA = j < JA;
+          const int og = warp + LOAD_WARPS * (isA ? j : j - JA);
+          if (og < (isA ? DA : DB) / 16) {
+            const int o4 = og * 4 + oq;
+            uint2 hi, lo;
+            tc::split4(v[eg * (JA + JB) + j], hi, lo);
+            const int lbo = isA ? (int)F::LBO_A : (int)F::LBO_B;
+            const int plane = isA ? F::A_PLANE : F::B_PLANE;
+            uint8_t* base = st + (isA ? 0 : 2 * F::A_PLANE);
+            const int off = (o4 >> 1) * (int)SBO + (edge >> 3) * lbo + (edge & 7) * 16 + (o4 & 1) * 8;
+            *reinterpret_cast<uint2*>(base + off) = hi;
+            *reinterpret_cast<uint2*>(base + plane + off) = lo;
+          }
         }
       }
       tc::fence_async_smem();
