@@ -29,14 +29,15 @@ static int g_debug_flags = 0;
 
 constexpr int BM = 128;       // rows per tile (UMMA M)
 constexpr int BK = 32;        // K per pipeline stage (2 UMMA K=16 steps)
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int EPI_WARPS = 4;
 constexpr int LOAD_WARPS = 8;
 constexpr int LOADERS = LOAD_WARPS * 32;
 constexpr int THREADS = 32 * (1 + EPI_WARPS + LOAD_WARPS);   // 416
 constexpr uint32_t LBO = 128;               // next 8-element K chunk
 constexpr uint32_t SBO = (BK / 8) * 128;    // next 8-row group (chunk-local image): 512 B
-constexpr int EPI_STRIDE = 36;              // floats; padded 32-column staging row
+constexpr int EPI_COLS = 128;               // columns staged per epilogue pass (BN < 128: BN)
+constexpr int EPI_STRIDE = EPI_COLS + 4;    // floats; padded staging row
 
 template <int BN>
 struct Cfg {
@@ -192,20 +193,28 @@ gemm_nt_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const uint8_t* _
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
       tc::mbar_wait(&tfull[acc], (lt >> 1) & 1);
       tc::fence_after_sync();
+      // EC columns at a time: TMEM -> registers -> warp-private staging (thread per row) -> the warp writes one
+      // row's EC contiguous floats per instruction (512 B for EC = 128): long contiguous runs for DRAM.
+      constexpr int EC = BN < EPI_COLS ? BN : EPI_COLS;
 #pragma unroll 1
-      for (int c0 = 0; c0 < ((dbg & 32) ? 0 : BN); c0 += 32) {
-        float v[32];
-        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+      for (int c0 = 0; c0 < ((dbg & 32) ? 0 : BN); c0 += EC) {
+#pragma unroll 1
+        for (int cc = 0; cc < EC; cc += 32) {
+          float v[32];
+          tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0 + cc), v);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(stg + lane * EPI_STRIDE + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(stg + lane * EPI_STRIDE + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
         __syncwarp();
-        const int c4 = (lane & 7) * 4;
+        constexpr int LPR = EC / 4;                          // lanes per row (float4 each): 32, 16 or 8
+        constexpr int RPI = 32 / LPR;                        // rows per store instruction
+        const int c4 = (lane % LPR) * 4;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + c4));
-#pragma unroll
-        for (int r8 = 0; r8 < 8; ++r8) {
-          const int r = r8 * 4 + (lane >> 3);
+#pragma unroll 4
+        for (int r0 = 0; r0 < 32; r0 += RPI) {
+          const int r = r0 + lane / LPR;
           const int gr = m0 + q * 32 + r;
           float4 o = *reinterpret_cast<const float4*>(stg + r * EPI_STRIDE + c4);
           o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
