@@ -71,12 +71,15 @@ def mlp_forward(layer: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
     """Linear -> norm -> SiLU.  On CUDA fp32 inputs the Linear (forward, data gradient, weight gradient) runs on
     the tcgen05 bf16x3 kernels when its shape is one the library supports (the angle/bond embeddings act on
     T = 276 480 rows per batch); norm and SiLU stay plain library layers."""
-    lin = layer[0]
+    lin, norm = layer[0], layer[1]
     if x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and ops.tc_linear_supported(lin.in_features, lin.out_features):
+        if (isinstance(norm, nn.BatchNorm1d) and norm.training and norm.momentum is not None and norm.affine
+                and torch.is_grad_enabled()):
+            return ops.mlp_bn_train(x, lin, norm)        # Linear + batch statistics + normalise + SiLU on library kernels
         h = ops.tc_linear(x, lin.weight, lin.bias)
     else:
         h = lin(x)
-    return layer[2](layer[1](h))
+    return layer[2](norm(h))
 
 
 class MLPLayer(nn.Module):

@@ -458,6 +458,54 @@ bn_backward_reduce_kernel(const float* __restrict__ R, const float* __restrict__
   block_reduce_to_partials<D, 2>(acc, partials + (int64_t)blockIdx.x * 2 * D, red);
 }
 
+// per-block partials {sum, sum of squares} per column of a tall [n, D] matrix: batch statistics of a
+// Linear -> BatchNorm1d(train) -> SiLU embedding layer (alignn.py:170-184).  Row layout [2][D] = what bn_finalize reads.
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+rowstats_partials_kernel(const float* __restrict__ a, int64_t n, float* __restrict__ partials) {
+  constexpr int V = RowCfg<D>::VPL;
+  __shared__ float red[kWarpsPerBlock * D];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  float acc[2][V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { acc[0][k] = 0.f; acc[1][k] = 0.f; }
+  for (int64_t r = warp0; r < n; r += nwarps) {
+    float v[V];
+    ld_row<D, false>(v, a + r * D, lane);
+#pragma unroll
+    for (int k = 0; k < V; ++k) { acc[0][k] += v[k]; acc[1][k] += v[k] * v[k]; }
+  }
+  block_reduce_to_partials<D, 2>(acc, partials + (int64_t)blockIdx.x * 2 * D, red);
+}
+
+// BatchNorm1d(train) + SiLU backward, pass 2: gR = scale * (gu - c1 - xhat * c2), gu = g_out * silu'(R*scale+shift)
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+bn_backward_apply_kernel(const float* __restrict__ R, const float* __restrict__ g_out, const float* __restrict__ scale,
+                         const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
+                         const float* __restrict__ c1, const float* __restrict__ c2, int64_t n, float* __restrict__ gR) {
+  constexpr int V = RowCfg<D>::VPL;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  float sc[V], sh[V], mu[V], rs[V], k1[V], k2[V];
+  ld_vec<D>(sc, scale, lane); ld_vec<D>(sh, shift, lane); ld_vec<D>(mu, mean, lane); ld_vec<D>(rs, rstd, lane);
+  ld_vec<D>(k1, c1, lane); ld_vec<D>(k2, c2, lane);
+  for (int64_t r = warp0; r < n; r += nwarps) {
+    float v[V], g[V], o[V];
+    ld_row<D, true>(v, R + r * D, lane);
+    ld_row<D, true>(g, g_out + r * D, lane);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float gu = g[k] * dsilu_(v[k] * sc[k] + sh[k]);
+      o[k] = sc[k] * (gu - k1[k] - (v[k] - mu[k]) * rs[k] * k2[k]);
+    }
+    st_row<D, true>(gR + r * D, o, lane);
+  }
+}
+
 // per-block partial column sums of a tall [n, D] matrix (bias gradients of the embedding Linears)
 template <int D>
 __global__ void __launch_bounds__(kThreads)
@@ -739,6 +787,26 @@ int alignn_b200_bn_backward_reduce(const float* R, const float* g_out, const flo
   if (partial_rows < grid) return ALIGNN_ERR_WORKSPACE;
   DISPATCH_D(d, alignn::bn_backward_reduce_kernel<D><<<grid, alignn::kThreads, 0, (cudaStream_t)stream>>>(
                     R, g_out, scale, shift, mean, rstd, n, partials));
+  return check_launch();
+}
+
+int alignn_b200_rowstats_partials(const float* a, int64_t n, int d, float* partials, int partial_rows, alignn_stream_t stream) {
+  if (!supported_d(d)) return ALIGNN_ERR_UNSUPPORTED_D;
+  if (n <= 0 || !a || !partials) return ALIGNN_ERR_BAD_ARG;
+  const int grid = grid_for_rows(n);
+  if (partial_rows < grid) return ALIGNN_ERR_WORKSPACE;
+  DISPATCH_D(d, alignn::rowstats_partials_kernel<D><<<grid, alignn::kThreads, 0, (cudaStream_t)stream>>>(a, n, partials));
+  return check_launch();
+}
+
+int alignn_b200_bn_backward_apply(const float* R, const float* g_out, const float* scale, const float* shift,
+                                  const float* mean, const float* rstd, const float* c1, const float* c2, int64_t n, int d,
+                                  float* gR, alignn_stream_t stream) {
+  if (!supported_d(d)) return ALIGNN_ERR_UNSUPPORTED_D;
+  if (n <= 0 || !R || !g_out || !scale || !shift || !mean || !rstd || !c1 || !c2 || !gR) return ALIGNN_ERR_BAD_ARG;
+  const int grid = grid_for_rows(n);
+  DISPATCH_D(d, alignn::bn_backward_apply_kernel<D><<<grid, alignn::kThreads, 0, (cudaStream_t)stream>>>(
+                    R, g_out, scale, shift, mean, rstd, c1, c2, n, gR));
   return check_launch();
 }
 

@@ -328,3 +328,57 @@ def tc_linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torc
     """nn.Linear forward/backward on the tensor-core kernels; the input width is zero-padded to a multiple of 32."""
     k_pad = (weight.shape[1] + 31) // 32 * 32
     return _TCLinearFn.apply(x, weight, bias, k_pad)
+
+
+# ---- Linear -> BatchNorm1d(train) -> SiLU (embedding MLP layers) ------------------------------------
+class _MLPBNTrainFn(torch.autograd.Function):
+    """One embedding layer in train mode, entirely on library kernels: tensor-core Linear, two-stage batch
+    statistics (fp64 finalize + running-stat update), fused normalise+SiLU, and the matching backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, bn, k_pad):
+        lib = _lib.load()
+        x = x.contiguous()
+        if k_pad != x.shape[1]:
+            x = torch.nn.functional.pad(x, (0, k_pad - x.shape[1]))
+            w = torch.nn.functional.pad(weight, (0, k_pad - weight.shape[1]))
+        else:
+            w = weight.contiguous()
+        R = gemm_nt(x, WeightImage(w), bias.contiguous())
+        n, d = R.shape
+        rows = partial_rows(n, d)
+        part = torch.empty(rows, 2, d, device=R.device, dtype=torch.float32)
+        _lib.check(lib.alignn_b200_rowstats_partials(ptr(R), n, d, ptr(part), rows, stream_ptr()), "alignn_b200_rowstats_partials")
+        track = bn.track_running_stats and bn.running_mean is not None
+        scale, shift, mean, rstd = bn_finalize(part, 0, n, gamma.contiguous(), beta.contiguous(), bn.eps, float(bn.momentum),
+                                               bn.running_mean if track else None, bn.running_var if track else None)
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        out = affine_silu_residual(R, None, scale, shift)
+        ctx.save_for_backward(x, w, R, scale, shift, mean, rstd)
+        ctx.k_in = weight.shape[1]
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, go):
+        lib = _lib.load()
+        x, w, R, scale, shift, mean, rstd = ctx.saved_tensors
+        go = go.contiguous()
+        n, d = R.shape
+        c1, c2 = bn_backward_reduce(R, go, scale, shift, mean, rstd)
+        gR = torch.empty_like(R)
+        _lib.check(lib.alignn_b200_bn_backward_apply(ptr(R), ptr(go), ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
+                                                     ptr(c1.contiguous()), ptr(c2.contiguous()), n, d, ptr(gR), stream_ptr()),
+                   "alignn_b200_bn_backward_apply")
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm_nt(gR, WeightImage(w, transpose=True))[:, :ctx.k_in]
+        gw = wgrad(gR, x, 1)[:, :ctx.k_in]
+        # a bias that feeds a train-mode BatchNorm has an identically zero gradient (sum_rows gR == 0)
+        return gx, gw, torch.zeros_like(c1), c2 * n, c1 * n, None, None
+
+
+def mlp_bn_train(x, lin, bn):
+    k_pad = (lin.in_features + 31) // 32 * 32
+    return _MLPBNTrainFn.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, bn, k_pad)

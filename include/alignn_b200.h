@@ -171,6 +171,16 @@ int alignn_b200_bn_backward_reduce(const float* R, const float* g_out, const flo
                                    const float* mean, const float* rstd, int64_t n, int d,
                                    float* partials, int partial_rows, alignn_stream_t stream);
 
+/* Linear -> BatchNorm1d(train) -> SiLU embedding layers (alignn.py:170-184) on rows [n,d]:
+ *   rowstats_partials: per-block {sum, sum^2} partials ([rows, 2, d]; feed alignn_b200_bn_finalize with which = 0,
+ *                      partial_stride = 2d), then alignn_b200_affine_silu_residual(res = NULL) applies norm + SiLU;
+ *   bn_backward_apply: gR = scale * (gu - c1 - xhat*c2), gu = g_out * silu'(R*scale+shift)  (c1, c2 from
+ *                      alignn_b200_bn_backward_reduce). */
+int alignn_b200_rowstats_partials(const float* a, int64_t n, int d, float* partials, int partial_rows, alignn_stream_t stream);
+int alignn_b200_bn_backward_apply(const float* R, const float* g_out, const float* scale, const float* shift,
+                                  const float* mean, const float* rstd, const float* c1, const float* c2, int64_t n, int d,
+                                  float* gR, alignn_stream_t stream);
+
 /* Per-block partial column sums of a tall contiguous [n, d] matrix (rows: alignn_b200_egc_partial_rows(n, d));
  * finish with alignn_b200_colsum.  Used for the bias gradients of the embedding Linears (alignn.py:201-222). */
 int alignn_b200_colsum_partials(const float* a, int64_t n, int d, float* partials, int partial_rows, alignn_stream_t stream);
