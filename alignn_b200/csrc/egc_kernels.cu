@@ -367,19 +367,19 @@ egc_backward_src_kernel(alignn_b200_egc_bwd_args a, float* __restrict__ partials
 // =============================================================================================
 // BatchNorm train-mode helpers
 // =============================================================================================
-// 32 channels per block x 8 row lanes; fp64 accumulation over the per-block partial rows, fixed order
-__global__ void __launch_bounds__(256)
+// 32 channels per block x 32 row lanes; fp64 accumulation over the per-block partial rows, fixed order
+__global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ partials, int rows, int stride, int which, double count,
                    int d, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                    float momentum, float* running_mean, float* running_var, float* scale, float* shift,
                    float* mean_out, float* rstd_out) {
-  __shared__ double ss[8][32], sq[8][32];
+  __shared__ double ss[32][33], sq[32][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   double s = 0.0, q = 0.0;
   if (c < d) {
     const float* p = partials + (size_t)which * 2 * d + c;
-    for (int r = rl; r < rows; r += 8) {
+    for (int r = rl; r < rows; r += 32) {
       s += (double)p[(size_t)r * stride];
       q += (double)p[(size_t)r * stride + d];
     }
@@ -388,7 +388,7 @@ bn_finalize_kernel(const float* __restrict__ partials, int rows, int stride, int
   __syncthreads();
   if (rl != 0 || c >= d) return;
 #pragma unroll
-  for (int k = 1; k < 8; ++k) { s += ss[k][cl]; q += sq[k][cl]; }
+  for (int k = 1; k < 32; ++k) { s += ss[k][cl]; q += sq[k][cl]; }
   const double mean = s / count;
   double var = q / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -415,18 +415,24 @@ affine_silu_residual_kernel(const float* __restrict__ R, const float* __restrict
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
   float sc[V], sh[V];
   ld_vec<D>(sc, scale, lane); ld_vec<D>(sh, shift, lane);
-  for (int64_t r = warp0; r < n; r += nwarps) {
-    float v[V], o[V];
+  for (int64_t r = warp0; r < n; r += 2 * nwarps) {   // two rows in flight per warp
+    const int64_t r2 = r + nwarps;
+    const bool has2 = r2 < n;
+    float v[V], v2[V], y[V], y2[V];
     ld_row<D, true>(v, R + r * D, lane);
-#pragma unroll
-    for (int k = 0; k < V; ++k) o[k] = silu_(v[k] * sc[k] + sh[k]);
+    if (has2) ld_row<D, true>(v2, R + r2 * D, lane);
     if (res) {
-      float y[V];
       ld_row<D, true>(y, res + r * D, lane);
-#pragma unroll
-      for (int k = 0; k < V; ++k) o[k] += y[k];
+      if (has2) ld_row<D, true>(y2, res + r2 * D, lane);
     }
-    st_row<D, true>(out + r * D, o, lane);
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = silu_(v[k] * sc[k] + sh[k]) + (res ? y[k] : 0.f);
+    st_row<D, true>(out + r * D, v, lane);
+    if (has2) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) v2[k] = silu_(v2[k] * sc[k] + sh[k]) + (res ? y2[k] : 0.f);
+      st_row<D, true>(out + r2 * D, v2, lane);
+    }
   }
 }
 
@@ -444,15 +450,29 @@ bn_backward_reduce_kernel(const float* __restrict__ R, const float* __restrict__
   ld_vec<D>(sc, scale, lane); ld_vec<D>(sh, shift, lane); ld_vec<D>(mu, mean, lane); ld_vec<D>(rs, rstd, lane);
 #pragma unroll
   for (int k = 0; k < V; ++k) { acc[0][k] = 0.f; acc[1][k] = 0.f; }
-  for (int64_t r = warp0; r < n; r += nwarps) {
-    float v[V], g[V];
+  for (int64_t r = warp0; r < n; r += 2 * nwarps) {   // two rows in flight per warp
+    const int64_t r2 = r + nwarps;
+    const bool has2 = r2 < n;
+    float v[V], g[V], v2[V], g2[V];
     ld_row<D, false>(v, R + r * D, lane);
     ld_row<D, false>(g, g_out + r * D, lane);
+    if (has2) {
+      ld_row<D, false>(v2, R + r2 * D, lane);
+      ld_row<D, false>(g2, g_out + r2 * D, lane);
+    }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       const float gu = g[k] * dsilu_(v[k] * sc[k] + sh[k]);
       acc[0][k] += gu;
       acc[1][k] += gu * (v[k] - mu[k]) * rs[k];
+    }
+    if (has2) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float gu = g2[k] * dsilu_(v2[k] * sc[k] + sh[k]);
+        acc[0][k] += gu;
+        acc[1][k] += gu * (v2[k] - mu[k]) * rs[k];
+      }
     }
   }
   block_reduce_to_partials<D, 2>(acc, partials + (int64_t)blockIdx.x * 2 * D, red);
@@ -527,22 +547,22 @@ colsum_partials_kernel(const float* __restrict__ a, int64_t n, float* __restrict
   block_reduce_to_partials<D, 1>(acc, partials + (int64_t)blockIdx.x * D, red);
 }
 
-// out[c] = alpha * sum_r a[r*stride + c]; 32 columns per block x 8 row lanes, fp64, fixed order.
+// out[c] = alpha * sum_r a[r*stride + c]; 32 columns per block x 32 row lanes, fp64, fixed order.
 // Used on per-block partial buffers (rows <= kMaxBlocks).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 colsum_kernel(const float* __restrict__ a, int64_t rows, int cols, int64_t stride, float alpha,
               float* __restrict__ out) {
-  __shared__ double ss[8][32];
+  __shared__ double ss[32][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   double s = 0.0;
   if (c < cols)
-    for (int64_t r = rl; r < rows; r += 8) s += (double)a[r * stride + c];
+    for (int64_t r = rl; r < rows; r += 32) s += (double)a[r * stride + c];
   ss[rl][cl] = s;
   __syncthreads();
   if (rl != 0 || c >= cols) return;
 #pragma unroll
-  for (int k = 1; k < 8; ++k) s += ss[k][cl];
+  for (int k = 1; k < 32; ++k) s += ss[k][cl];
   out[c] = alpha * (float)s;
 }
 
@@ -717,7 +737,7 @@ int alignn_b200_bn_finalize(const float* partials, int partial_rows, int partial
   if (!partials || !scale || !shift || !mean || !rstd || partial_rows <= 0 || d <= 0 || count <= 0 ||
       (which != 0 && which != 1) || ((running_mean == nullptr) != (running_var == nullptr)))
     return ALIGNN_ERR_BAD_ARG;
-  alignn::bn_finalize_kernel<<<(d + 31) / 32, 256, 0, (cudaStream_t)stream>>>(
+  alignn::bn_finalize_kernel<<<(d + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(
       partials, partial_rows, partial_stride, which, (double)count, d, gamma, beta, eps, momentum, running_mean,
       running_var, scale, shift, mean, rstd);
   return check_launch();
@@ -822,7 +842,7 @@ int alignn_b200_colsum_partials(const float* a, int64_t n, int d, float* partial
 int alignn_b200_colsum(const float* a, int64_t rows, int cols, int64_t stride, float alpha, float* out,
                        alignn_stream_t stream) {
   if (!a || !out || rows < 0 || cols <= 0 || stride < cols) return ALIGNN_ERR_BAD_ARG;
-  alignn::colsum_kernel<<<(cols + 31) / 32, 256, 0, (cudaStream_t)stream>>>(a, rows, cols, stride, alpha, out);
+  alignn::colsum_kernel<<<(cols + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(a, rows, cols, stride, alpha, out);
   return check_launch();
 }
 
