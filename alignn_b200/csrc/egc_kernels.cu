@@ -62,16 +62,10 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
         my_e = a.in_eid ? a.in_eid[base + lane] : base + lane;
         my_s = a.src[my_e];
       }
-      for (int i = 0; i < cnt; ++i) {
-        const int64_t e = __shfl_sync(0xffffffffu, my_e, i);
-        const int64_t s = __shfl_sync(0xffffffffu, my_s, i);
-        float g[V], av[V], cv[V], m[V];
-        ld_row<D, true>(g, a.G + e * D, lane);
-        ld_row<D, false>(av, a.P + s * 4 * D, lane);
-        ld_row<D, false>(cv, a.P + s * 4 * D + D, lane);
+      // everything of one edge after its three rows have arrived
+      auto edge_tail = [&](int64_t e, float (&m)[V], const float (&cv)[V]) {
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-          m[k] = av[k] + bv[k] + g[k];
           const float sg = sigmoidf_(m[k]);
           accS[k] += sg;
           accSh[k] += cv[k] * sg;
@@ -103,6 +97,32 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
           }
           st_row<D, true>(a.y_out + e * D, o, lane);
         }
+      };
+      int i = 0;
+      for (; i + 1 < cnt; i += 2) {   // two edges (six row loads) in flight per warp
+        const int64_t e0 = __shfl_sync(0xffffffffu, my_e, i), s0 = __shfl_sync(0xffffffffu, my_s, i);
+        const int64_t e1 = __shfl_sync(0xffffffffu, my_e, i + 1), s1 = __shfl_sync(0xffffffffu, my_s, i + 1);
+        float g0[V], a0[V], c0[V], g1[V], a1[V], c1[V];
+        ld_row<D, true>(g0, a.G + e0 * D, lane);
+        ld_row<D, true>(g1, a.G + e1 * D, lane);
+        ld_row<D, false>(a0, a.P + s0 * 4 * D, lane);
+        ld_row<D, false>(a1, a.P + s1 * 4 * D, lane);
+        ld_row<D, false>(c0, a.P + s0 * 4 * D + D, lane);
+        ld_row<D, false>(c1, a.P + s1 * 4 * D + D, lane);
+#pragma unroll
+        for (int k = 0; k < V; ++k) { g0[k] += a0[k] + bv[k]; g1[k] += a1[k] + bv[k]; }
+        edge_tail(e0, g0, c0);
+        edge_tail(e1, g1, c1);
+      }
+      if (i < cnt) {
+        const int64_t e0 = __shfl_sync(0xffffffffu, my_e, i), s0 = __shfl_sync(0xffffffffu, my_s, i);
+        float g0[V], a0[V], c0[V];
+        ld_row<D, true>(g0, a.G + e0 * D, lane);
+        ld_row<D, false>(a0, a.P + s0 * 4 * D, lane);
+        ld_row<D, false>(c0, a.P + s0 * 4 * D + D, lane);
+#pragma unroll
+        for (int k = 0; k < V; ++k) g0[k] += a0[k] + bv[k];
+        edge_tail(e0, g0, c0);
       }
     }
     // ---- node finalize: h = Sh/(S+eps); x' = src_update(x) + h; norm; silu; residual -----------
@@ -342,7 +362,23 @@ egc_backward_src_kernel(alignn_b200_egc_bwd_args a, float* __restrict__ partials
         my_e = a.out_eid[base + lane];
         my_t = a.dst[my_e];
       }
-      for (int i = 0; i < cnt; ++i) {
+      int i = 0;
+      for (; i + 1 < cnt; i += 2) {   // two edges (six row loads) in flight per warp
+        const int64_t e0 = __shfl_sync(0xffffffffu, my_e, i), t0 = __shfl_sync(0xffffffffu, my_t, i);
+        const int64_t e1 = __shfl_sync(0xffffffffu, my_e, i + 1), t1 = __shfl_sync(0xffffffffu, my_t, i + 1);
+        float gm0[V], m0[V], gs0[V], gm1[V], m1[V], gs1[V];
+        ld_row<D, false>(gm0, a.GM + e0 * D, lane);
+        ld_row<D, false>(gm1, a.GM + e1 * D, lane);
+        ld_row<D, true>(m0, a.M + e0 * D, lane);
+        ld_row<D, true>(m1, a.M + e1 * D, lane);
+        ld_row<D, false>(gs0, a.GSh + t0 * D, lane);
+        ld_row<D, false>(gs1, a.GSh + t1 * D, lane);
+#pragma unroll
+        for (int k = 0; k < V; ++k) { accA[k] += gm0[k]; accC[k] += gs0[k] * sigmoidf_(m0[k]); }
+#pragma unroll
+        for (int k = 0; k < V; ++k) { accA[k] += gm1[k]; accC[k] += gs1[k] * sigmoidf_(m1[k]); }
+      }
+      if (i < cnt) {
         const int64_t e = __shfl_sync(0xffffffffu, my_e, i);
         const int64_t t = __shfl_sync(0xffffffffu, my_t, i);
         float gm[V], m[V], gsh[V];
