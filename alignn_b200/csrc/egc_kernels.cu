@@ -247,6 +247,7 @@ egc_backward_dst_kernel(alignn_b200_egc_bwd_args a) {
   extern __shared__ __align__(16) float dyn_smem[];
   float* sacc = dyn_smem;                                  // [kWarpsPerBlock][6][D]
   float* nvec = dyn_smem + kWarpsPerBlock * 6 * D;         // node norm vectors  [6][D]
+  float* sseg = nvec + 12 * D;                             // [kWarpsPerBlock][2][D]: dL/dSh, dL/dS of the warp's segment
   float* evec = nvec + 6 * D;                              // edge norm vectors  [6][D]
   {
     const float* srcs[12] = {a.n_w, a.n_b, a.n_mean, a.n_rstd, a.n_c1, a.n_c2, a.e_w, a.e_b, a.e_mean, a.e_rstd, a.e_c1, a.e_c2};
@@ -262,9 +263,10 @@ egc_backward_dst_kernel(alignn_b200_egc_bwd_args a) {
   for (int i = lane; i < 6 * D; i += 32) acc[i] = 0.f;
   __syncwarp();
 
+  float* wseg = sseg + wib * 2 * D;
   for (int64_t v = warp0; v < a.Nn; v += nwarps) {
-    float gsh[V], gs[V];
     {  // node side
+      float gsh[V], gs[V];
       float xp[V], go[V], gxp[V], sv[V], hv[V];
       ld_row<D, false>(xp, a.XP + v * D, lane);
       ld_row<D, false>(go, a.gx_out + v * D, lane);
@@ -280,6 +282,16 @@ egc_backward_dst_kernel(alignn_b200_egc_bwd_args a) {
       }
       smem_row_add<D>(acc + 4 * D, gxp, lane);
       st_row<D, false>(a.GSh + v * D, gsh, lane);
+      // parked in shared memory for the edge loop (each lane re-reads only what it wrote)
+      using C2 = RowCfg<D>;
+#pragma unroll
+      for (int c = 0; c < C2::CH; ++c)
+#pragma unroll
+        for (int j = 0; j < C2::W; ++j) {
+          wseg[c * 32 * C2::W + lane * C2::W + j] = gsh[c * C2::W + j];
+          wseg[D + c * 32 * C2::W + lane * C2::W + j] = gs[c * C2::W + j];
+        }
+      __syncwarp();
     }
     float accB[V];
 #pragma unroll
@@ -292,27 +304,46 @@ egc_backward_dst_kernel(alignn_b200_egc_bwd_args a) {
         my_e = a.in_eid ? a.in_eid[base + lane] : base + lane;
         my_s = a.src[my_e];
       }
+      // software pipeline: the M / gy_out rows of edge i+1 are requested before edge i is processed
+      float m[V], go[V];
+      if (cnt > 0) {
+        const int64_t e = __shfl_sync(0xffffffffu, my_e, 0);
+        ld_row<D, true>(m, a.M + e * D, lane);
+        if (a.gy_out) ld_row<D, true>(go, a.gy_out + e * D, lane);
+      }
       for (int i = 0; i < cnt; ++i) {
         const int64_t e = __shfl_sync(0xffffffffu, my_e, i);
         const int64_t s = __shfl_sync(0xffffffffu, my_s, i);
-        float m[V], cv[V], gm[V];
-        ld_row<D, true>(m, a.M + e * D, lane);
+        float cv[V], gm[V], mn[V], gon[V];
         ld_row<D, false>(cv, a.P + s * 4 * D + D, lane);
+        const bool more = (i + 1 < cnt);
+        if (more) {
+          const int64_t en = __shfl_sync(0xffffffffu, my_e, i + 1);
+          ld_row<D, true>(mn, a.M + en * D, lane);
+          if (a.gy_out) ld_row<D, true>(gon, a.gy_out + en * D, lane);
+        }
         if (a.gy_out) {
-          float go[V];
-          ld_row<D, true>(go, a.gy_out + e * D, lane);
           norm_backward_row<D, NORM>(m, go, a.ln_eps, evec, gm, acc, acc + D, lane);
         } else {
 #pragma unroll
           for (int k = 0; k < V; ++k) gm[k] = 0.f;
         }
+        {
+          float gsh[V], gs[V];
+          ld_srow<D>(gsh, wseg, lane);
+          ld_srow<D>(gs, wseg + D, lane);
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-          const float sg = sigmoidf_(m[k]);
-          gm[k] += (gsh[k] * cv[k] + gs[k]) * sg * (1.f - sg);
-          accB[k] += gm[k];
+          for (int k = 0; k < V; ++k) {
+            const float sg = sigmoidf_(m[k]);
+            gm[k] += (gsh[k] * cv[k] + gs[k]) * sg * (1.f - sg);
+            accB[k] += gm[k];
+          }
         }
         st_row<D, false>(a.GM + e * D, gm, lane);   // re-read by the src-keyed pass and the GEMMs
+        if (more) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) { m[k] = mn[k]; go[k] = gon[k]; }
+        }
       }
     }
     st_row<D, false>(a.GP + v * 4 * D + 2 * D, accB, lane);
@@ -812,7 +843,7 @@ int alignn_b200_egc_backward(const alignn_b200_egc_bwd_args* a) {
   if (a->norm_nodes != a->norm_edges) return ALIGNN_ERR_BAD_ARG;   // both norms of a conv are of one kind (alignn.py:71-76)
 #define LAUNCH_BWD_DST(NORM)                                                                                   \
   DISPATCH_D(a->d, {                                                                                           \
-    const size_t smem_bytes = (size_t)(alignn::kWarpsPerBlock * 6 + 12) * D * sizeof(float);                   \
+    const size_t smem_bytes = (size_t)(alignn::kWarpsPerBlock * 8 + 12) * D * sizeof(float);                   \
     static bool configured = false;                                                                            \
     if (!configured) {                                                                                         \
       cudaError_t e = cudaFuncSetAttribute(alignn::egc_backward_dst_kernel<D, NORM>,                           \

@@ -223,7 +223,7 @@ inline int ctas_for(int64_t K, int groups) {
   int per_group = kNumSMsWgrad / groups;
   if (per_group < 1) per_group = 1;
   const int64_t chunks = (K + BK - 1) / BK;
-  const int64_t want = (chunks + 3) / 4;          // at least ~4 pipeline stages of work per CTA
+  const int64_t want = (chunks + 3) / 4;          // at least ~4 pipeline stages of work per CTA (fewer, larger slabs measured no faster)
   if (want < per_group) per_group = (int)(want < 1 ? 1 : want);
   return per_group;
 }
