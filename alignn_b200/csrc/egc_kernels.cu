@@ -35,7 +35,7 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-  const bool train = a.M != nullptr;
+  const bool train = a.XP != nullptr;      // (M is a null pointer for an edgeless graph, so XP marks training)
   const bool stats = a.partials != nullptr;
   {
     const float* srcs[4] = {a.n_w, a.n_b, a.e_w, a.e_b};
@@ -70,7 +70,7 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
           accS[k] += sg;
           accSh[k] += cv[k] * sg;
         }
-        if (train) st_row<D, true>(a.M + e * D, m, lane);
+        if (train) st_row<D, true>(a.M + e * D, m, lane);   // Ne > 0 here, so M is a real buffer
         if (a.norm_edges == ALIGNN_NORM_STATS) {
           smem_row_add<D>(st, m, lane);
 #pragma unroll
@@ -786,8 +786,8 @@ int alignn_b200_egc_forward(const alignn_b200_egc_fwd_args* a) {
   if (a->residual && ((a->norm_nodes != ALIGNN_NORM_STATS && !a->x) ||
                       (a->norm_edges != ALIGNN_NORM_STATS && a->y_out && !a->y))) return ALIGNN_ERR_BAD_ARG;
   if ((a->norm_nodes == ALIGNN_NORM_STATS || a->norm_edges == ALIGNN_NORM_STATS) && !a->partials) return ALIGNN_ERR_BAD_ARG;
-  if ((a->norm_nodes == ALIGNN_NORM_STATS || a->norm_edges == ALIGNN_NORM_STATS) && !a->M) return ALIGNN_ERR_BAD_ARG;
-  if (a->M && (!a->XP || !a->S || !a->H)) return ALIGNN_ERR_BAD_ARG;
+  if ((a->norm_nodes == ALIGNN_NORM_STATS || a->norm_edges == ALIGNN_NORM_STATS) && !a->XP) return ALIGNN_ERR_BAD_ARG;
+  if (a->XP && (!a->S || !a->H || (a->Ne > 0 && !a->M))) return ALIGNN_ERR_BAD_ARG;   // training: all saved buffers
   cudaStream_t st = (cudaStream_t)a->stream;
   const int grid = grid_for_rows(a->Nn);
   DISPATCH_D(a->d, {

@@ -100,7 +100,8 @@ typedef struct {
   float* x_out;   /* [Nn,d]; may be NULL when norm_nodes == STATS */
   float* y_out;   /* [Ne,d]; NULL = edge output not needed (dead output / STATS) */
   float* M;       /* [Ne,d] pre-norm gate m (alignn.py:101); NULL in inference */
-  float* XP;      /* [Nn,d] pre-norm node update x' (alignn.py:110); NULL in inference */
+  float* XP;      /* [Nn,d] pre-norm node update x' (alignn.py:110); NULL in inference.  XP != NULL selects
+                     training mode (M, S, H are then required; M may be NULL only when Ne == 0) */
   float* S;       /* [Nn,d] sum_sigma (alignn.py:108); NULL in inference */
   float* H;       /* [Nn,d] h = sum_sigma_h / (sum_sigma + eps) (alignn.py:109); NULL in inference */
   /* STATS mode: per-block partial column sums, [partial_rows, 4, d] = {sum m, sum m^2, sum x', sum x'^2} */

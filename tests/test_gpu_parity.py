@@ -256,3 +256,23 @@ def test_atomwise_energy_and_forces_vs_reference_golden(golden_dir):
     off = g.node_graph_offsets().tolist()
     for a, b in zip(off[:-1], off[1:]):
         assert float(res["grad"][a:b].sum(0).abs().max()) < 1e-4
+
+
+def test_edgeless_graph_and_single_node():
+    """Empty edge set (isolated atoms): sums over no edges are 0 (alignn.py:105-109); nothing may read out of bounds."""
+    g = Graph(np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), 5)
+    d = 64
+    x, y = GI.features(1, 5, d), torch.zeros(0, d)
+    for norm in ("layernorm", "batchnorm"):
+        conv = _make_conv(norm, d, 11, True)
+        xi = x.to(DEV).requires_grad_(True)
+        xo, yo = conv(g.to(DEV), xi, y.to(DEV))
+        xo.sum().backward()
+        oc = O.EdgeGatedGraphConv(d, d, norm=norm).double()
+        GI.fill_state_dict(oc, 11)
+        xr = x.double().requires_grad_(True)
+        xo_ref, _ = oc(to_oracle(g), xr, y.double())
+        xo_ref.sum().backward()
+        assert yo.shape == (0, d)
+        assert_close(xo, xo_ref, what=f"edgeless {norm} x_out")
+        assert_close(xi.grad, xr.grad, what=f"edgeless {norm} gx", atol=1e-5)

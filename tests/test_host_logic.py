@@ -175,3 +175,26 @@ def test_state_dict_names_match_reference_layout():
     assert (cfg.alignn_layers, cfg.gcn_layers, cfg.hidden_features, cfg.atom_input_features) == (4, 4, 256, 92)
     with pytest.raises(Exception):
         ALIGNNConfig(name="not_alignn")
+
+
+def test_as_graph_adapts_dglgraph_like_objects():
+    """A DGLGraph-like object (here: the pure-torch DGL stand-in used for golden generation) is accepted at the
+    boundary: structure is read once through the DGL API subset and the sorted-CSR index is cached on it."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "dgl_stub"))
+    try:
+        import dgl
+    finally:
+        sys.path.pop(0)
+    from alignn_b200.graph import as_graph
+    g, _, _, _ = synthetic.make_batch(batch_size=2, atoms=5, k=4, seed=4)
+    s, d = g.edges()
+    dg = dgl.DGLGraph(s.long(), d.long(), g.num_nodes(), g.batch_num_nodes().clone(), g.batch_num_edges().clone())
+    dg.ndata["atom_features"] = g.ndata["atom_features"]
+    dg.edata["r"] = g.edata["r"]
+    ours = as_graph(dg)
+    assert torch.equal(ours.index.in_ptr, g.index.in_ptr) and torch.equal(ours.index.out_eid, g.index.out_eid)
+    assert ours.batch_size == 2 and "r" in ours.edata and "atom_features" in ours.ndata
+    assert as_graph(dg) is ours                       # cached on the DGL object
+    assert as_graph(g) is g
+    with pytest.raises(TypeError):
+        as_graph(object())
