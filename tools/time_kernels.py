@@ -44,3 +44,11 @@ for (K, D, G) in [(276480, 256, 1), (23040, 256, 4), (23040, 256, 1), (1920, 256
     t = timeit(lambda: ops.wgrad(A, B, G))
     t_ref = timeit(lambda: A.t() @ B)
     print(f"wgrad K={K} D={D} groups={G}: {t:8.1f} us ({4.0 * K * D * (G + 1) / t / 1e3:7.1f} GB/s)   torch fp32 {t_ref:8.1f} us")
+# residual epilogue (data-gradient GEMMs: gy = gy_out + GM W)
+for (M, N, K) in [(276480, 256, 256), (23040, 256, 1024)]:
+    A = torch.randn(M, K, device=dev)
+    W = torch.randn(N, K, device=dev) / K ** 0.5
+    R = torch.randn(M, N, device=dev)
+    img = ops.WeightImage(W)
+    t = timeit(lambda: ops.gemm_nt(A, img, None, R))
+    print(f"gemm_nt+residual M={M} N={N} K={K}: {t:8.1f} us ({4.0 * (M * K + 2 * M * N) / t / 1e3:7.1f} GB/s)")
