@@ -308,6 +308,7 @@ def run_ours(args):
         out = model((g, lg, lat))
         loss = (out - tgt).abs().mean()
         loss.backward()
+        reducer.gather()                                      # gradients -> flat buffer (one multi-tensor copy)
         return loss
 
     if use_graph:
@@ -333,7 +334,7 @@ def run_ours(args):
     def run_resident(i):
         if use_graph:
             graphs_res[i % nb][0].replay()
-            reducer.all_reduce()
+            reducer.reduce_flat()
             graph_opt.replay()
         else:
             step(resident[i % nb])
@@ -342,7 +343,7 @@ def run_ours(args):
         if use_graph:
             gr, loss_b = graphs_e2e[i % nb]
             gr.replay()
-            reducer.all_reduce()
+            reducer.reduce_flat()
             graph_opt.replay()
             return loss_b.item()                              # D2H + sync, as train.py:300-305 does
         return step(h2d(i)).item()

@@ -106,4 +106,7 @@ def test_single_process_is_a_noop_group():
     g0 = m.a.weight.grad
     assert g0.data_ptr() >= red.flat.data_ptr()                   # grads are views into the flat buffer
     red.zero_grad()
-    assert float(m.a.weight.grad.abs().sum()) == 0.0
+    assert m.a.weight.grad is None                                 # autograd writes fresh gradients next step
+    m(torch.randn(4, 6)).sum().backward()
+    red.all_reduce()
+    assert m.a.weight.grad.data_ptr() == g0.data_ptr()             # ... which land in the same flat slice
