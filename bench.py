@@ -393,8 +393,11 @@ def run_ours(args):
     roofline = None
     if k:
         ach = k["bytes"] / (k["avg_ms"] * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture per round
+        # (profiles/r01_ncu_full_summary.md: 383.6 + 302.6 MB in BatchNorm-train mode); unknown for other modes
+        traffic = 686.2e6 if args.norm == "batchnorm" and (N, E, T) == (1920, 23040, 276480) else None
         roofline = {"bound": "hbm", "kernel": "egc_forward_kernel<256> on L(g) (Nn=E, Ne=T)", "achieved": ach,
-                    "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                     "avg_launch_ms": k["avg_ms"], "launches_timed": k["launches"], "algorithmic_bytes_per_launch": k["bytes"]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
