@@ -8,9 +8,11 @@ with identical attribute / state_dict names so reference chec
 with `load_state_dict`.
 
 The four node Linear layers run as ONE [Nn,d]x[d,4d] GEMM and the edge gate as one [Ne,d]x[d,d]
-GEMM; everything else of the layer -- u_add_v, sigmoid, both update_all reductions, the division,
-both norms, SiLU, residuals -- is a single fused CUDA kernel forward and two backward
-(alignn_b200/csrc/egc_kernels.cu), called through the C ABI.
+GEMM, both on the tcgen05 bf16x3 tensor-core kernel (csrc/gemm_tc.cu); everything else of the layer --
+u_add_v, sigmoid, both update_all reductions, the division, both norms, SiLU, residuals -- is a single
+fused CUDA kernel forward and two backward (csrc/egc_kernels.cu); data gradients reuse the GEMM kernel with
+transposed weight images, weight gradients run on the split-K tensor-core kernel (csrc/wgrad_tc.cu).  All of
+it is reached through the C ABI (include/alignn_b200.h).
 """
 from __future__ import annotations
 

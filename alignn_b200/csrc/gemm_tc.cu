@@ -32,7 +32,6 @@ constexpr int BK = 32;        // K per pipeline stage (2 UMMA K=16 steps)
 constexpr int STAGES = 3;
 constexpr int EPI_WARPS = 4;
 constexpr int LOAD_WARPS = 8;
-constexpr int LOADERS = LOAD_WARPS * 32;
 constexpr int THREADS = 32 * (1 + EPI_WARPS + LOAD_WARPS);   // 416
 constexpr uint32_t LBO = 128;               // next 8-element K chunk
 constexpr uint32_t SBO = (BK / 8) * 128;    // next 8-row group (chunk-local image): 512 B
@@ -104,15 +103,13 @@ gemm_nt_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const uint8_t* _
     // recomputed index math (an earlier version spent ~3000 cycles per chunk on it).
     constexpr int PF = 3;
     float4 buf[PF][4];
-    int row[4], soff[4];
+    int soff[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      int kq;
-      a_coord(i, lt, row[i], kq);
-      soff[i] = plane_off(row[i], kq * 4);
+      int row, kq;
+      a_coord(i, lt, row, kq);
+      soff[i] = plane_off(row, kq * 4);
     }
-    int kq0;
-    { int r_; a_coord(0, lt, r_, kq0); }                 // kq of load 0; loads 1..3 share kq parity pattern
     const int my_tiles = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int nchunks = my_tiles * nk;
     // load cursor (runs PF chunks ahead of the store cursor)
