@@ -290,3 +290,33 @@ def energy_and_forces(model: ALIGNN, g: OGraph, lg: OGraph, energy_mult_natoms=T
     f_ij = zeros.index_add(0, g.src, pair_forces)     # copy_e/sum on reverse(g)  (:555-562)
     # result['out'] is the un-multiplied per-graph output (alignn_atomwise.py:653); en_out drives forces
     return out.detach(), (f_ji - f_ij).detach(), pair_forces.detach()
+
+
+def radius_graph(lattice_mat, cart_coords, cutoff=5.0, bond_tol=0.5, atol=1e-5, cutoff_extra=0.5):
+    """Periodic radius graph, alignn/graphs.py:267-364, on torch tensors (cartesian_prod + cdist + where).
+
+    Returns (u, v, r, cell_images) like the reference; retries with a larger cutoff until the highest-numbered
+    atom has a bond (the reference's `g.num_nodes() == len(atoms.elements)` test, :347-350)."""
+    import math
+    X = torch.as_tensor(cart_coords, dtype=torch.float64)
+    lat = torch.as_tensor(lattice_mat, dtype=torch.float64)
+    frac = X @ torch.linalg.inv(lat)
+    n = X.shape[0]
+    while True:
+        recp = 2 * math.pi * torch.linalg.inv(lat).T                       # :291
+        recp_len = torch.sqrt(torch.sum(recp ** 2, dim=1))
+        maxr = torch.ceil((cutoff + bond_tol) * recp_len / (2 * math.pi))  # :295
+        nmin = torch.floor(torch.min(frac, dim=0)[0]) - maxr
+        nmax = torch.ceil(torch.max(frac, dim=0)[0]) + maxr
+        ranges = [torch.arange(float(a), float(b), dtype=torch.float64) for a, b in zip(nmin, nmax)]
+        cells = torch.cartesian_prod(*ranges)                              # :304
+        X_dst = ((cells @ lat)[:, None, :] + X).reshape(-1, 3)             # :308-311
+        dist = torch.cdist(X, X_dst, compute_mode="donot_use_mm_for_euclid_dist")
+        mask = (dist <= cutoff) & ~torch.isclose(dist, torch.zeros(1, dtype=torch.float64), atol=atol)   # :318-325
+        u, v = torch.where(mask)
+        images = cells[v // n]
+        r = (X_dst[v] - X[u]).float()
+        v = v % n
+        if u.numel() and int(max(u.max(), v.max())) + 1 == n:
+            return u, v, r, images
+        cutoff += cutoff_extra

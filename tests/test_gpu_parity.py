@@ -276,3 +276,4 @@ def test_edgeless_graph_and_single_node():
         assert yo.shape == (0, d)
         assert_close(xo, xo_ref, what=f"edgeless {norm} x_out")
         assert_close(xi.grad, xr.grad, what=f"edgeless {norm} gx", atol=1e-5)
+

@@ -1,0 +1,47 @@
+"""CPU: the host-side periodic radius-graph builder (feeds BASELINE config 4) against the oracle restatement of
+alignn/graphs.py:267-364, bond for bond and in the same order."""
+import numpy as np
+import pytest
+import torch
+
+from alignn_b200 import neighbors
+from oracle import alignn_oracle as O
+
+
+def _random_cell(seed, n, skew=0.3):
+    rng = np.random.default_rng(seed)
+    lat = np.eye(3) * (4.0 + 2.0 * rng.random(3)) + skew * rng.normal(size=(3, 3))
+    frac = rng.random((n, 3))
+    return lat, frac @ lat
+
+
+@pytest.mark.parametrize("seed,n,cutoff", [(1, 1, 5.0), (2, 2, 4.0), (3, 7, 4.5), (4, 12, 3.5)])
+def test_radius_graph_matches_reference_algorithm(seed, n, cutoff):
+    lat, X = _random_cell(seed, n)
+    u, v, r, im = neighbors.radius_graph(lat, X, cutoff=cutoff, block=3)
+    uo, vo, ro, imo = O.radius_graph(lat, X, cutoff=cutoff)
+    assert np.array_equal(u, uo.numpy()) and np.array_equal(v, vo.numpy())          # same bonds, same order
+    assert np.array_equal(im, imo.numpy())
+    np.testing.assert_allclose(r, ro.numpy(), rtol=0, atol=1e-5)
+    d = np.linalg.norm(r, axis=1)
+    assert d.min() > 1e-5 and d.max() <= max(cutoff, d.max())                        # no self distance
+    # every bond has its reverse (same multiset of displacement lengths per unordered pair)
+    fwd = sorted(zip(u.tolist(), v.tolist(), np.round(d, 4).tolist()))
+    rev = sorted(zip(v.tolist(), u.tolist(), np.round(d, 4).tolist()))
+    assert fwd == rev
+
+
+def test_diamond_supercell_is_16_coordinated_within_4_angstrom():
+    """Diamond Si: 4 first + 12 second neighbours inside 4 A (E = 16 N, T = sum deg^2)."""
+    lat, X = neighbors.diamond_supercell(reps=2)
+    assert X.shape == (64, 3)
+    g, lg = neighbors.crystal_graph(lat, X, torch.zeros(64, 92), cutoff=4.0)
+    assert g.num_edges() == 64 * 16
+    indeg = torch.bincount(g.edges()[1].long(), minlength=64)
+    assert int(indeg.min()) == 16 and int(indeg.max()) == 16
+    assert lg.num_edges() == 64 * 16 * 16                     # no self loops in g -> every (i, j) pair kept
+    assert lg.index.dst_sorted
+    h = lg.edata["h"]
+    assert float(h.min()) >= -1.0 and float(h.max()) <= 1.0
+    # tetrahedral angle between first-neighbour bonds: cos = -1/3 must occur
+    assert torch.isclose(h, torch.tensor(-1.0 / 3.0), atol=1e-5).any()
