@@ -47,26 +47,29 @@ class EdgeIndex:
 
     @staticmethod
     def build(src: np.ndarray, dst: np.ndarray, num_nodes: int) -> "EdgeIndex":
-        """Stable counting sort by dst and by src.  Bit-exact vs oracle.csr_by_key."""
-        src = np.ascontiguousarray(src, dtype=np.int64)
-        dst = np.ascontiguousarray(dst, dtype=np.int64)
+        """Stable counting sort by dst and by src (native: alignn_b200_csr_build_host).  Bit-exact vs
+        oracle.csr_by_key."""
+        from . import _lib
+        lib = _lib.load()
+        src = np.ascontiguousarray(src, dtype=np.int64).reshape(-1)
+        dst = np.ascontiguousarray(dst, dtype=np.int64).reshape(-1)
         E = src.shape[0]
         if E >= 2 ** 31 or num_nodes >= 2 ** 31:
             raise ValueError("graph too large for int32 edge index")
-        if E and (src.min() < 0 or dst.min() < 0 or src.max() >= num_nodes or dst.max() >= num_nodes):
+        if dst.shape[0] != E:
+            raise ValueError("src and dst differ in length")
+        i32 = lambda k: np.empty(k, dtype=np.int32)  # noqa: E731
+        s32, d32, in_ptr, in_eid, out_ptr, out_eid = i32(E), i32(E), i32(num_nodes + 1), i32(E), i32(num_nodes + 1), i32(E)
+        flags = np.zeros(2, dtype=np.int32)
+        p = lambda a: a.ctypes.data  # noqa: E731
+        rc = lib.alignn_b200_csr_build_host(p(src), p(dst), num_nodes, E, p(s32), p(d32), p(in_ptr), p(in_eid),
+                                            p(out_ptr), p(out_eid), p(flags[0:1]), p(flags[1:2]))
+        if rc == -1:
             raise ValueError("edge endpoint out of range")
-        indeg = np.bincount(dst, minlength=num_nodes)
-        outdeg = np.bincount(src, minlength=num_nodes)
-        in_ptr = np.zeros(num_nodes + 1, dtype=np.int64)
-        out_ptr = np.zeros(num_nodes + 1, dtype=np.int64)
-        np.cumsum(indeg, out=in_ptr[1:])
-        np.cumsum(outdeg, out=out_ptr[1:])
-        dst_sorted = bool(E == 0 or np.all(dst[1:] >= dst[:-1]))
-        in_eid = np.arange(E, dtype=np.int64) if dst_sorted else np.argsort(dst, kind="stable")
-        out_eid = np.argsort(src, kind="stable")
-        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32))  # noqa: E731
-        return EdgeIndex(t(src), t(dst), t(in_ptr), t(in_eid), t(out_ptr), t(out_eid),
-                         dst_sorted, int(indeg.max()) if E else 0, num_nodes)
+        _lib.check(rc, "alignn_b200_csr_build_host")
+        t = torch.from_numpy
+        return EdgeIndex(t(s32), t(d32), t(in_ptr), t(in_eid), t(out_ptr), t(out_eid),
+                         bool(flags[0]), int(flags[1]), num_nodes)
 
     _FIELDS = ("src", "dst", "in_ptr", "in_eid", "out_ptr", "out_eid")
 
@@ -199,20 +202,22 @@ class Graph:
         """
         if not backtracking:
             raise NotImplementedError("backtracking=False is not used by the reference")
+        from . import _lib
+        lib = _lib.load()
         ix = self.index
-        src = ix.src.cpu().numpy().astype(np.int64)
-        in_ptr = ix.in_ptr.cpu().numpy().astype(np.int64)
-        in_eid = ix.in_eid.cpu().numpy().astype(np.int64)
+        src = np.ascontiguousarray(ix.src.cpu().numpy())
+        in_ptr = np.ascontiguousarray(ix.in_ptr.cpu().numpy())
+        in_eid = np.ascontiguousarray(ix.in_eid.cpu().numpy())
         E = src.shape[0]
-        deg = in_ptr[src + 1] - in_ptr[src]                 # candidates i for each j
-        lj = np.repeat(np.arange(E, dtype=np.int64), deg)
-        start = np.repeat(in_ptr[src], deg)
-        off = np.arange(lj.shape[0], dtype=np.int64) - np.repeat(np.cumsum(deg) - deg, deg)
-        li = in_eid[start + off]
-        keep = li != lj                                      # only self-loop bonds pair with themselves
-        li, lj = li[keep], lj[keep]
-        eoff = np.cumsum(self._bne.numpy())
-        lbne = np.bincount(np.searchsorted(eoff, lj, side="right"), minlength=len(eoff))
+        p = lambda a: a.ctypes.data  # noqa: E731
+        T = int(lib.alignn_b200_line_graph_count_host(p(src), p(in_ptr), p(in_eid), E))
+        if T < 0:
+            raise RuntimeError("alignn_b200_line_graph_count_host failed")
+        li, lj = np.empty(T, dtype=np.int64), np.empty(T, dtype=np.int64)
+        bne = np.ascontiguousarray(self._bne.numpy(), dtype=np.int64)
+        lbne = np.zeros(bne.shape[0], dtype=np.int64)
+        _lib.check(lib.alignn_b200_line_graph_build_host(p(src), p(in_ptr), p(in_eid), E, p(bne), bne.shape[0], T,
+                                                         p(li), p(lj), p(lbne)), "alignn_b200_line_graph_build_host")
         lg = Graph(li, lj, E, self._bne.clone(), lbne)
         if self.device.type != "cpu":
             lg = lg.to(self.device)

@@ -225,6 +225,26 @@ size_t alignn_b200_wgrad_workspace_bytes(int64_t K, int DA, int DB, int groups);
 int alignn_b200_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int DA, int DB, int groups,
                       float* out, int64_t ld_out, void* workspace, size_t workspace_bytes, alignn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Host-side structure builders (plain CPU code, host pointers, no stream; usable without a GPU).
+ * Replace the structure step DGL does on the CPU for the reference: `dgl.graph((u, v))` + CSR/CSC views
+ * (alignn/graphs.py:544) and `g.line_graph(shared=True)` (alignn/graphs.py:588).  Integer-exact.
+ *
+ * csr_build_host: int64 (src, dst) -> int32 copies + stable sorted-CSR index (in_* by destination, out_* by
+ *   source), whether the edge list is already destination-sorted, and the largest in-degree.
+ * line_graph_count_host / line_graph_build_host: L(g) edges (i -> j) iff dst(i) == src(j), i != j, emitted
+ *   destination-major (j ascending, then i ascending); `capacity` must equal the count; per-graph edge counts of
+ *   L(g) are written to l_batch_num_edges[batch_size] from the per-graph bond counts of g.
+ * ---------------------------------------------------------------------------------------- */
+int alignn_b200_csr_build_host(const int64_t* src, const int64_t* dst, int64_t num_nodes, int64_t num_edges,
+                               int32_t* src32, int32_t* dst32, int32_t* in_ptr, int32_t* in_eid, int32_t* out_ptr,
+                               int32_t* out_eid, int32_t* dst_sorted, int32_t* max_in_degree);
+int64_t alignn_b200_line_graph_count_host(const int32_t* src, const int32_t* in_ptr, const int32_t* in_eid,
+                                          int64_t num_edges);
+int alignn_b200_line_graph_build_host(const int32_t* src, const int32_t* in_ptr, const int32_t* in_eid,
+                                      int64_t num_edges, const int64_t* batch_num_edges, int64_t batch_size,
+                                      int64_t capacity, int64_t* lsrc, int64_t* ldst, int64_t* l_batch_num_edges);
+
 /* Per-graph mean over node rows (dgl.nn.AvgPooling, alignn.py:325) and its backward. */
 int alignn_b200_segment_mean(const float* x, const int32_t* graph_ptr /*[B+1]*/, int64_t B, int d, float* out,
                              alignn_stream_t stream);

@@ -198,3 +198,22 @@ def test_as_graph_adapts_dglgraph_like_objects():
     assert as_graph(g) is g
     with pytest.raises(TypeError):
         as_graph(object())
+
+
+def test_native_structure_builders_edge_cases():
+    """alignn_b200_csr_build_host / line_graph_*_host on degenerate inputs."""
+    g = Graph(np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), 5)
+    assert g.num_edges() == 0 and g.index.in_ptr.tolist() == [0] * 6 and g.index.max_in_deg == 0
+    lg = g.line_graph(shared=True)
+    assert lg.num_nodes() == 0 and lg.num_edges() == 0
+    with pytest.raises(ValueError):
+        Graph([0, 7], [1, 2], 3)
+    # a batch whose second crystal has no bonds: per-graph line-graph counts still add up
+    a = Graph([0, 1], [1, 0], 2)
+    b = Graph(np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), 3)
+    c = Graph([0, 1, 1, 2], [1, 0, 2, 1], 3)
+    bg = batch([a, b, c])
+    lg = bg.line_graph()
+    assert lg.batch_num_edges().tolist() == [2, 0, 6] and lg.num_nodes() == 6
+    olg = O.line_graph(to_oracle(bg))
+    assert sorted(zip(lg.edges()[0].tolist(), lg.edges()[1].tolist())) == sorted(zip(olg.src.tolist(), olg.dst.tolist()))
