@@ -83,6 +83,9 @@ _SIGNATURES = {
     "alignn_b200_csr_build_host": (C.c_int, [_fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
     "alignn_b200_line_graph_count_host": (C.c_int64, [_fp, _fp, _fp, C.c_int64]),
     "alignn_b200_line_graph_build_host": (C.c_int, [_fp, _fp, _fp, C.c_int64, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp]),
+    "alignn_b200_radius_graph_count_host": (C.c_int64, [_fp, _fp, C.c_int64, C.c_int64, C.c_double, C.c_double]),
+    "alignn_b200_radius_graph_build_host": (C.c_int, [_fp, _fp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int64, _fp,
+                                                      _fp, _fp, _fp]),
     "alignn_b200_segment_mean": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, _fp, _fp]),
     "alignn_b200_segment_mean_backward": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, _fp, _fp]),
 }

@@ -91,3 +91,78 @@ int alignn_b200_line_graph_build_host(const int32_t* src, const int32_t* in_ptr,
 }
 
 }  // extern "C"
+
+// -------------------------------------------------------------------------------------------------
+// Periodic radius graph (alignn/graphs.py:267-364): bond u -> v for every (atom u of the home cell, periodic image
+// `c` of atom v) with atol < |x_v + shift_c - x_u| <= cutoff, emitted in (u, c, v) order -- the order torch.where
+// gives on the reference's [N, images*N] mask.  `shifts` are the cartesian image offsets (cells @ lattice), computed
+// by the caller so that the arithmetic matches the restatement bit for bit.  Double precision, same operation
+// order as the numpy/torch restatements: d = (shift + x_v) - x_u ; dist = sqrt((dx*dx + dy*dy) + dz*dz).
+// -------------------------------------------------------------------------------------------------
+#include <cmath>
+
+namespace {
+template <bool kFill>
+int64_t radius_scan(const double* X, const double* shifts, int64_t n, int64_t n_images, double cutoff, double atol,
+                    int64_t capacity, int64_t* u_out, int64_t* v_out, int64_t* c_out, float* r_out) {
+  int64_t t = 0;
+  // bounding box of the home cell's atoms: an image whose shifted box is farther than the cutoff (plus a guard
+  // band for rounding) from x_u cannot hold a neighbour and is skipped as a whole -- pure pruning, the bonds found
+  // and their order are unchanged
+  double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  for (int64_t v = 0; v < n; ++v)
+    for (int k = 0; k < 3; ++k) {
+      const double x = X[3 * v + k];
+      if (v == 0 || x < lo[k]) lo[k] = x;
+      if (v == 0 || x > hi[k]) hi[k] = x;
+    }
+  const double reach = cutoff * (1.0 + 1e-9) + 1e-9;
+  for (int64_t u = 0; u < n; ++u) {
+    const double xu = X[3 * u], yu = X[3 * u + 1], zu = X[3 * u + 2];
+    const double pu[3] = {xu, yu, zu};
+    for (int64_t c = 0; c < n_images; ++c) {
+      const double sx = shifts[3 * c], sy = shifts[3 * c + 1], sz = shifts[3 * c + 2];
+      double gap2 = 0.0;
+      for (int k = 0; k < 3; ++k) {
+        const double a = lo[k] + shifts[3 * c + k], b = hi[k] + shifts[3 * c + k];
+        const double g = pu[k] < a ? a - pu[k] : (pu[k] > b ? pu[k] - b : 0.0);
+        gap2 += g * g;
+      }
+      if (gap2 > reach * reach) continue;
+      for (int64_t v = 0; v < n; ++v) {
+        const double dx = (sx + X[3 * v]) - xu, dy = (sy + X[3 * v + 1]) - yu, dz = (sz + X[3 * v + 2]) - zu;
+        const double dist = std::sqrt((dx * dx + dy * dy) + dz * dz);
+        if (dist <= cutoff && !(std::fabs(dist) <= atol)) {
+          if (kFill) {
+            if (t >= capacity) return -1;
+            u_out[t] = u; v_out[t] = v; c_out[t] = c;
+            r_out[3 * t] = (float)dx; r_out[3 * t + 1] = (float)dy; r_out[3 * t + 2] = (float)dz;
+          }
+          ++t;
+        }
+      }
+    }
+  }
+  return t;
+}
+}  // namespace
+
+extern "C" {
+
+int64_t alignn_b200_radius_graph_count_host(const double* cart_coords, const double* shifts, int64_t num_atoms,
+                                            int64_t num_images, double cutoff, double atol) {
+  if (num_atoms < 0 || num_images < 0 || (num_atoms > 0 && !cart_coords) || (num_images > 0 && !shifts)) return -1;
+  return radius_scan<false>(cart_coords, shifts, num_atoms, num_images, cutoff, atol, 0, nullptr, nullptr, nullptr, nullptr);
+}
+
+int alignn_b200_radius_graph_build_host(const double* cart_coords, const double* shifts, int64_t num_atoms,
+                                        int64_t num_images, double cutoff, double atol, int64_t capacity, int64_t* u,
+                                        int64_t* v, int64_t* image_index, float* r) {
+  if (num_atoms < 0 || num_images < 0 || capacity < 0 || (num_atoms > 0 && !cart_coords) || (num_images > 0 && !shifts))
+    return ALIGNN_ERR_BAD_ARG;
+  if (capacity > 0 && (!u || !v || !image_index || !r)) return ALIGNN_ERR_BAD_ARG;
+  const int64_t t = radius_scan<true>(cart_coords, shifts, num_atoms, num_images, cutoff, atol, capacity, u, v, image_index, r);
+  return t == capacity ? ALIGNN_OK : ALIGNN_ERR_WORKSPACE;
+}
+
+}  // extern "C"

@@ -245,6 +245,16 @@ int alignn_b200_line_graph_build_host(const int32_t* src, const int32_t* in_ptr,
                                       int64_t num_edges, const int64_t* batch_num_edges, int64_t batch_size,
                                       int64_t capacity, int64_t* lsrc, int64_t* ldst, int64_t* l_batch_num_edges);
 
+/* Periodic radius graph on the host (alignn/graphs.py:267-364): bonds (u, image c of v) with
+ * atol < |x_v + shifts[c] - x_u| <= cutoff in (u, c, v) order; r = displacement (fp32), image_index = c.
+ * `shifts` [num_images,3] = cell offsets @ lattice (computed by the caller).  Two-pass: count, then build with
+ * capacity == count. */
+int64_t alignn_b200_radius_graph_count_host(const double* cart_coords, const double* shifts, int64_t num_atoms,
+                                            int64_t num_images, double cutoff, double atol);
+int alignn_b200_radius_graph_build_host(const double* cart_coords, const double* shifts, int64_t num_atoms,
+                                        int64_t num_images, double cutoff, double atol, int64_t capacity, int64_t* u,
+                                        int64_t* v, int64_t* image_index, float* r);
+
 /* Per-graph mean over node rows (dgl.nn.AvgPooling, alignn.py:325) and its backward. */
 int alignn_b200_segment_mean(const float* x, const int32_t* graph_ptr /*[B+1]*/, int64_t B, int d, float* out,
                              alignn_stream_t stream);

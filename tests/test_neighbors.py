@@ -18,7 +18,7 @@ def _random_cell(seed, n, skew=0.3):
 @pytest.mark.parametrize("seed,n,cutoff", [(1, 1, 5.0), (2, 2, 4.0), (3, 7, 4.5), (4, 12, 3.5)])
 def test_radius_graph_matches_reference_algorithm(seed, n, cutoff):
     lat, X = _random_cell(seed, n)
-    u, v, r, im = neighbors.radius_graph(lat, X, cutoff=cutoff, block=3)
+    u, v, r, im = neighbors.radius_graph(lat, X, cutoff=cutoff)
     uo, vo, ro, imo = O.radius_graph(lat, X, cutoff=cutoff)
     assert np.array_equal(u, uo.numpy()) and np.array_equal(v, vo.numpy())          # same bonds, same order
     assert np.array_equal(im, imo.numpy())
