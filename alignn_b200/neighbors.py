@@ -63,10 +63,17 @@ def radius_graph(lattice_mat, cart_coords, cutoff: float = 5.0, bond_tol: float 
         cutoff += cutoff_extra
 
 
-def crystal_graph(lattice_mat, cart_coords, atom_features: torch.Tensor, cutoff: float = 4.0):
+def crystal_graph(lattice_mat, cart_coords, atom_features: torch.Tensor, cutoff: float = 4.0,
+                  neighbor_strategy: str = "radius_graph", max_neighbors: int = 12):
     """(g, lg) for one periodic structure, laid out like `Graph.atom_dgl_multigraph` output (graphs.py:472-592):
-    g.ndata['atom_features'], g.edata['r'], lg = L(g) with lg.edata['h'] = bond cosines."""
-    u, v, r, _ = radius_graph(lattice_mat, cart_coords, cutoff=cutoff)
+    g.ndata['atom_features'], g.edata['r'], lg = L(g) with lg.edata['h'] = bond cosines.
+    `neighbor_strategy` is the reference's switch (graphs.py:497-536): "radius_graph" or "k-nearest"."""
+    if neighbor_strategy == "k-nearest":
+        u, v, r, _ = knn_graph(lattice_mat, cart_coords, max_neighbors=max_neighbors, cutoff=cutoff)
+    elif neighbor_strategy == "radius_graph":
+        u, v, r, _ = radius_graph(lattice_mat, cart_coords, cutoff=cutoff)
+    else:
+        raise ValueError(f"Not implemented yet: neighbor_strategy={neighbor_strategy!r}")
     g = Graph(u, v, int(np.asarray(cart_coords).shape[0]))
     g.ndata["atom_features"] = atom_features
     g.edata["r"] = torch.from_numpy(r)
@@ -87,3 +94,75 @@ def diamond_supercell(reps: int = 5, a: float = 5.431, jitter: float = 0.0, seed
     if jitter:
         X = X + np.random.default_rng(seed).normal(scale=jitter, size=X.shape)
     return lat, X
+
+
+def _all_neighbors(lat, X, cutoff, atol=1e-8):
+    """Every (u, v, image, distance) with 0 < |x_v + image@lat - x_u| <= cutoff (what jarvis'
+    `Atoms.get_all_neighbors(r=cutoff)` lists per site), from the native scan."""
+    from . import _lib
+    lib = _lib.load()
+    n = X.shape[0]
+    recp_len = np.sqrt(((2 * math.pi * np.linalg.inv(lat).T) ** 2).sum(1))
+    maxr = np.ceil(cutoff * recp_len / (2 * math.pi)) + 1
+    ranges = [np.arange(-m, m + 1, dtype=np.float64) for m in maxr]
+    cells = np.stack(np.meshgrid(*ranges, indexing="ij"), -1).reshape(-1, 3)
+    sh = np.ascontiguousarray(cells @ lat)
+    Xc = np.ascontiguousarray(X)
+    p = lambda a: a.ctypes.data  # noqa: E731
+    cnt = int(lib.alignn_b200_radius_graph_count_host(p(Xc), p(sh), n, sh.shape[0], float(cutoff), float(atol)))
+    u, v, ci = (np.empty(cnt, dtype=np.int64) for _ in range(3))
+    r = np.empty((cnt, 3), dtype=np.float32)
+    _lib.check(lib.alignn_b200_radius_graph_build_host(p(Xc), p(sh), n, sh.shape[0], float(cutoff), float(atol), cnt,
+                                                       p(u), p(v), p(ci), p(r)), "alignn_b200_radius_graph_build_host")
+    img = cells[ci].astype(np.int64)
+    d = (X[v] + img @ lat) - X[u]
+    return u, v, img, np.sqrt((d ** 2).sum(1))
+
+
+def knn_graph(lattice_mat, cart_coords, max_neighbors: int = 12, cutoff: float = 8.0):
+    """k-nearest-neighbour crystal graph with shell completion, made undirected the reference's way
+    (`nearest_neighbor_edges` + `build_undirected_edgedata`, alignn/graphs.py:155-264, `use_canonize=True`).
+
+    Per atom: neighbours within `cutoff` sorted by distance; everything out to the distance of the k-th one is kept
+    (whole shells, so the degree is >= k); if some atom has fewer than k neighbours the cutoff grows to max(a, b, c)
+    or doubles (:170-186).  Each kept pair is canonised to (min id, max id, image of the second atom relative to the
+    first) and every canonical bond emits BOTH directions adjacently, (u, v, d) then (v, u, -d) (:253-257).
+    Self-image bonds appear with +image and -image as two canonical bonds, as in the reference.
+    Bond order: canonical pairs in order of first encounter (atoms ascending, neighbours by (distance, v, image)),
+    images of one pair in lexicographic order -- the reference's order inside a pair is Python-set iteration order
+    and not reproducible; no model output depends on it.
+    Returns (u, v, r[float32], images[int64]).
+    """
+    lat = np.asarray(lattice_mat, dtype=np.float64)
+    X = np.asarray(cart_coords, dtype=np.float64)
+    n = X.shape[0]
+    abc = np.linalg.norm(lat, axis=1)
+    while True:
+        u, v, img, dist = _all_neighbors(lat, X, cutoff)
+        counts = np.bincount(u, minlength=n)
+        if counts.min() >= max_neighbors:
+            break
+        cutoff = float(abc.max()) if cutoff < abc.max() else 2 * cutoff
+    order = np.lexsort((img[:, 2], img[:, 1], img[:, 0], v, dist, u))     # by u, then distance, then (v, image)
+    u, v, img, dist = u[order], v[order], img[order], dist[order]
+    start = np.concatenate([[0], np.cumsum(counts)])
+    kth = dist[start[:-1] + max_neighbors - 1]                             # distance of the k-th neighbour per atom
+    keep = dist <= kth[u]
+    u, v, img = u[keep], v[keep], img[keep]
+    swap = v < u                                                           # canonize_edge (:127-152)
+    cu, cv = np.where(swap, v, u), np.where(swap, u, v)
+    cimg = np.where(swap[:, None], -img, img)
+    pairs = {}
+    for a, b, im in zip(cu.tolist(), cv.tolist(), map(tuple, cimg.tolist())):
+        pairs.setdefault((a, b), set()).add(im)
+    uu, vv, rr, ii = [], [], [], []
+    frac = X @ np.linalg.inv(lat)
+    for (a, b), ims in pairs.items():
+        for im in sorted(ims):
+            d = (frac[b] + np.asarray(im, dtype=np.float64) - frac[a]) @ lat   # :245-249
+            uu += [a, b]
+            vv += [b, a]
+            rr += [d, -d]
+            ii += [im, im]
+    return (np.asarray(uu, dtype=np.int64), np.asarray(vv, dtype=np.int64), np.asarray(rr, dtype=np.float32),
+            np.asarray(ii, dtype=np.int64).reshape(-1, 3))

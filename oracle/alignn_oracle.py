@@ -320,3 +320,51 @@ def radius_graph(lattice_mat, cart_coords, cutoff=5.0, bond_tol=0.5, atol=1e-5, 
         if u.numel() and int(max(u.max(), v.max())) + 1 == n:
             return u, v, r, images
         cutoff += cutoff_extra
+
+
+def knn_graph(lattice_mat, cart_coords, max_neighbors=12, cutoff=8.0):
+    """k-NN crystal graph, alignn/graphs.py:155-264 with use_canonize=True, in plain Python (small cells only).
+
+    `atoms.get_all_neighbors(r)` (jarvis-tools, absent) is restated as a brute-force search over periodic images.
+    Ties are broken by (distance, v, image) and the images of one canonical pair are emitted in sorted order (the
+    reference's order there is Python-set iteration order)."""
+    import itertools
+    from collections import OrderedDict
+    lat = np.asarray(lattice_mat, dtype=np.float64)
+    X = np.asarray(cart_coords, dtype=np.float64)
+    n = X.shape[0]
+    abc = np.linalg.norm(lat, axis=1)
+    frac = X @ np.linalg.inv(lat)
+    while True:
+        reach = [int(np.ceil(cutoff / h)) + 1 for h in (abs(np.linalg.det(lat)) / np.array(
+            [np.linalg.norm(np.cross(lat[1], lat[2])), np.linalg.norm(np.cross(lat[2], lat[0])),
+             np.linalg.norm(np.cross(lat[0], lat[1]))]))]
+        nbrs = [[] for _ in range(n)]
+        for im in itertools.product(*[range(-m, m + 1) for m in reach]):
+            shift = np.asarray(im, dtype=np.float64) @ lat
+            for i in range(n):
+                d = np.sqrt((((X + shift) - X[i]) ** 2).sum(1))
+                for j in np.nonzero((d <= cutoff) & (d > 1e-8))[0]:
+                    nbrs[i].append((float(d[j]), int(j), tuple(int(t) for t in im)))
+        if min(len(l) for l in nbrs) >= max_neighbors:                     # :166-186
+            break
+        cutoff = float(abc.max()) if cutoff < abc.max() else 2 * cutoff
+    edges = OrderedDict()
+    for i, lst in enumerate(nbrs):
+        lst = sorted(lst)                                                  # :202 (distance, then v, image)
+        max_dist = lst[max_neighbors - 1][0]                               # :208
+        for dist, j, im in lst:
+            if dist > max_dist:                                            # :212-214 keep the whole shell
+                continue
+            a, b, img = (i, j, im) if j >= i else (j, i, tuple(-t for t in im))   # canonize_edge :127-152
+            edges.setdefault((a, b), set()).add(img)
+    u, v, r, images = [], [], [], []
+    for (a, b), ims in edges.items():                                      # :240-257
+        for im in sorted(ims):
+            d = (frac[b] + np.asarray(im, dtype=np.float64) - frac[a]) @ lat
+            for uu, vv, dd in ((a, b, d), (b, a, -d)):
+                u.append(uu)
+                v.append(vv)
+                r.append(dd)
+                images.append(im)
+    return (np.asarray(u), np.asarray(v), np.asarray(r, dtype=np.float32), np.asarray(images).reshape(-1, 3))

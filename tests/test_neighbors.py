@@ -45,3 +45,29 @@ def test_diamond_supercell_is_16_coordinated_within_4_angstrom():
     assert float(h.min()) >= -1.0 and float(h.max()) <= 1.0
     # tetrahedral angle between first-neighbour bonds: cos = -1/3 must occur
     assert torch.isclose(h, torch.tensor(-1.0 / 3.0), atol=1e-5).any()
+
+
+@pytest.mark.parametrize("seed,n,k", [(1, 1, 12), (2, 2, 12), (3, 5, 8), (4, 9, 12)])
+def test_knn_graph_matches_reference_algorithm(seed, n, k):
+    """k-NN strategy (the reference default, graphs.py:155-264): same bonds in the same order as the plain-Python
+    restatement; both directions adjacent; every atom keeps whole shells (degree >= k)."""
+    lat, X = _random_cell(seed, n, skew=0.2)
+    u, v, r, im = neighbors.knn_graph(lat, X, max_neighbors=k, cutoff=4.0)
+    uo, vo, ro, imo = O.knn_graph(lat, X, max_neighbors=k, cutoff=4.0)
+    assert np.array_equal(u, uo) and np.array_equal(v, vo) and np.array_equal(im, imo)
+    np.testing.assert_allclose(r, ro, atol=1e-5)
+    assert np.array_equal(u[0::2], v[1::2]) and np.array_equal(v[0::2], u[1::2])     # reverse bond adjacent
+    np.testing.assert_allclose(r[0::2], -r[1::2], atol=1e-6)
+    assert np.bincount(v, minlength=n).min() >= k
+
+
+def test_knn_graph_on_diamond_gives_first_two_shells():
+    lat, X = neighbors.diamond_supercell(reps=2)
+    u, v, r, im = neighbors.knn_graph(lat, X, max_neighbors=12, cutoff=8.0)
+    deg = np.bincount(v, minlength=64)
+    # 4 + 12: the 12th neighbour lies in the second shell.  Like the reference (`if dist > max_dist`, graphs.py:212)
+    # the shell test compares doubles exactly, so second-shell members whose distance rounds 1 ulp above the 12th
+    # one are dropped unless the partner atom kept the bond: degrees land between 12 and 16.
+    assert deg.min() >= 12 and deg.max() <= 16
+    d = np.linalg.norm(r, axis=1)
+    assert np.allclose(np.unique(np.round(d, 3)), [2.352, 3.840])
