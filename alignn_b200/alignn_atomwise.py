@@ -92,6 +92,25 @@ class ALIGNNAtomWiseConfig(BaseSettings):
     additional_output_weight: float = 0
 
 
+EV_PER_A3_IN_GPA = 160.21766208          # 1 eV/A^3 in GPa (alignn_atomwise.py:569)
+
+
+def virial_stress(r: torch.Tensor, pair_forces: torch.Tensor, node_offsets: torch.Tensor, batch_num_edges,
+                  V: torch.Tensor, multiplier: float = 1.0) -> torch.Tensor:
+    """Per-crystal virial stress [B,3,3] = multiplier * -160.21766208 * (r_b^T @ F_b) / V_b, where r_b / F_b are the
+    bond vectors and pair forces of crystal b and V_b is the volume stored on its FIRST atom
+    (alignn_atomwise.py:610-635: the loop reads `g.ndata["V"][count_node + 0]`).
+    One [E,9] outer product and one segment sum over the batch instead of the reference's per-graph matmul loop."""
+    E = r.shape[0]
+    bne = torch.as_tensor(batch_num_edges, device=r.device).long()
+    B = bne.numel()
+    gid = torch.repeat_interleave(torch.arange(B, device=r.device), bne, output_size=E)
+    outer = (r.unsqueeze(2) * pair_forces.unsqueeze(1)).reshape(E, 9)
+    virial = torch.zeros(B, 9, device=r.device, dtype=r.dtype).index_add_(0, gid, outer).view(B, 3, 3)
+    vol = V.to(r.dtype)[node_offsets[:-1].long()].view(B, 1, 1)
+    return multiplier * (-EV_PER_A3_IN_GPA * virial / vol)
+
+
 class ALIGNNAtomWise(nn.Module):
     """Energy (+ forces by autograd through the CUDA conv stack) -- the inference path of ALIGNN-FF
     (alignn/models/alignn_atomwise.py:249-660, BASELINE config 4).
@@ -99,14 +118,17 @@ class ALIGNNAtomWise(nn.Module):
     Same constructor/`forward((g, lg, lat))`/result-dict surface and state_dict names as the reference.
     Forces use first-order autograd only (`create_graph=False`): the conv's autograd Function is
     once-differentiable, so FF *training* on forces (double backward, :536) is not available.
-    Not built yet: stress (:567-638), include_pos_deriv, cutoff-function variants.
+    Stress: the batched virial of :610-638 (`batch_stress=True`, the default) from the same pair forces.
+    Not built: `batch_stress=False` (:573-590), include_pos_deriv, cutoff-function variants.
     """
 
     def __init__(self, config: ALIGNNAtomWiseConfig = ALIGNNAtomWiseConfig(name="alignn_atomwise")):
         super().__init__()
         c = self.config = config
         for flag, why in ((c.include_pos_deriv, "include_pos_deriv"), (c.use_cutoff_function, "use_cutoff_function"),
-                          (c.stresswise_weight != 0, "stresswise_weight != 0"), (c.extra_features != 0, "extra_features")):
+                          (c.stresswise_weight != 0 and not c.batch_stress, "stresswise_weight != 0 with batch_stress=False"),
+                          (c.stresswise_weight != 0 and not c.calculate_gradient, "stress without calculate_gradient"),
+                          (c.extra_features != 0, "extra_features")):
             if flag:
                 raise NotImplementedError(f"alignn_b200.ALIGNNAtomWise: {why} is outside the built hot path")
         self.classification = c.classification
@@ -168,6 +190,7 @@ class ALIGNNAtomWise(nn.Module):
         if c.atomwise_output_features > 0 and c.atomwise_weight != 0:
             atomwise_pred = self.fc_atomwise(x)
         forces = torch.empty(1)
+        stress = torch.empty(1)
         natoms = g.batch_num_nodes().to(out.device).to(out.dtype)
         en_out = out * natoms if c.energy_mult_natoms else out + 0.0   # (:495-497; no aliasing of `out`, cf. App. D-12)
         if c.use_penalty:                                               # (:498-510) zero for bonds >= threshold
@@ -187,11 +210,14 @@ class ALIGNNAtomWise(nn.Module):
                 forces = forces - zeros.index_add(0, src, pair_forces)   # ... minus over out-edges (:555-563)
             forces = torch.squeeze(forces)
             result["pair_forces"] = pair_forces
+            if c.stresswise_weight != 0:
+                stress = virial_stress(r.detach(), pair_forces, g.node_graph_offsets(), g.batch_num_edges(),
+                                       g.ndata["V"], c.stress_multiplier)
         if c.link == "log":
             out = torch.exp(out)
         elif c.link == "logit":
             out = torch.sigmoid(out)
         if self.classification:
             out = self.softmax(out)
-        result.update(out=out, additional=additional, grad=forces, stresses=torch.empty(1), atomwise_pred=atomwise_pred)
+        result.update(out=out, additional=additional, grad=forces, stresses=stress, atomwise_pred=atomwise_pred)
         return result

@@ -292,6 +292,19 @@ def energy_and_forces(model: ALIGNN, g: OGraph, lg: OGraph, energy_mult_natoms=T
     return out.detach(), (f_ji - f_ij).detach(), pair_forces.detach()
 
 
+def virial_stress(g: OGraph, pair_forces, V, stress_multiplier=1.0):
+    """Batched virial stress, alignn_atomwise.py:610-635: for crystal b, -(160.21766208 * r_b^T @ F_b / V[first atom
+    of b]) -- the loop adds `num_nodes = 0` to `count_node` before indexing V, i.e. it reads the first atom's volume."""
+    r = g.edata["r"]
+    out, ce, cn = [], 0, 0
+    for b in range(len(g.bne)):
+        ne = int(g.bne[b])
+        out.append(-1 * (160.21766208 * torch.matmul(r[ce:ce + ne].T, pair_forces[ce:ce + ne]) / V[cn]))
+        ce += ne
+        cn += int(g.bnn[b])
+    return stress_multiplier * torch.stack(out)
+
+
 def radius_graph(lattice_mat, cart_coords, cutoff=5.0, bond_tol=0.5, atol=1e-5, cutoff_extra=0.5):
     """Periodic radius graph, alignn/graphs.py:267-364, on torch tensors (cartesian_prod + cdist + where).
 

@@ -68,3 +68,9 @@ def checksum(*arrays) -> int:
 # JVASP-98225 (32 atoms: 16 K + 16 Bi) cartesian coordinates are read by make_golden.py
 # from the reference test (alignn/tests/test_force_reduction.py:22-55) at generation time
 # and stored inside tests/golden/jvasp_98225.npz; tests read them from there.
+
+
+def cell_volumes(batch_num_nodes) -> torch.Tensor:
+    """g.ndata["V"] (graphs.py:560): the cell volume repeated on every atom of a crystal; crystal b gets 90 + 17 b A^3."""
+    bnn = [int(n) for n in batch_num_nodes]
+    return torch.cat([torch.full((n,), 90.0 + 17.0 * b) for b, n in enumerate(bnn)])

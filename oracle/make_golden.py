@@ -240,6 +240,21 @@ def main():
                         pair_forces=pair.numpy())
     print("atomwise_small ok: E =", g.num_edges(), "T =", lg.num_edges())
 
+    # same batch with the stress head on (alignn_atomwise.py:567-638, batch_stress=True); V = cell volume on every atom
+    vols = GI.cell_volumes(g.batch_num_nodes())
+    gg.ndata["V"] = vols.to(dtype)
+    ref_s = ref_atomwise.ALIGNNAtomWise(ref_atomwise.ALIGNNAtomWiseConfig(
+        name="alignn_atomwise", **{**acfg, "stresswise_weight": 0.1, "stress_multiplier": 10.0})).to(dtype)
+    GI.fill_state_dict(ref_s, 400)
+    res_s = ref_s((gg, ll, lat.to(dtype)))
+    assert (res_s["grad"] - res["grad"]).abs().max() < 1e-12
+    st = O.virial_stress(og_, pair, vols.to(dtype), stress_multiplier=10.0)
+    assert (st - res_s["stresses"].detach()).abs().max() < 1e-11 * st.abs().max()
+    np.savez_compressed(os.path.join(OUT, "atomwise_stress.npz"),
+                        in_crc=GI.checksum(*g.edges(), g.edata["r"], vols),
+                        stresses=res_s["stresses"].detach().numpy(), pair_forces=pair.numpy())
+    print("atomwise_stress ok:", tuple(res_s["stresses"].shape))
+
     # ---------------------------------------------------------------- reference test properties (fp64)
     # tests/test_force_reduction.py:212-229 restated on the real reference conv + stub graph ops.
     torch.set_default_dtype(torch.float64)
