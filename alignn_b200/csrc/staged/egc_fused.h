@@ -1,0 +1,58 @@
+/* STAGED WORK -- not part of libalignn_b200.so, not declared in include/alignn_b200.h.
+ *
+ * One-kernel forward of the edge side of EdgeGatedGraphConv (alignn/models/alignn.py:100-109,123,127):
+ * the edge-gate Linear (`self.edge_gate(edge_feats)`, :101) runs on tcgen05 into TMEM and the gate / segment-sum
+ * epilogue consumes the accumulator there, so G = edge_gate(y) never exists in HBM (DESIGN.md "known deviations"
+ * item 1).  Written in round 1 after the GPU budget was spent: compiles for sm_100a, has NOT run on hardware yet.
+ * tools/build_staged.py builds it into alignn_b200/csrc/staged/libalignn_b200_staged.so; tests/test_gpu_staged.py
+ * (opt-in: ALIGNN_B200_STAGED=1) compares it bit for bit with the shipped two-kernel path.
+ */
+#ifndef ALIGNN_B200_STAGED_EGC_FUSED_H
+#define ALIGNN_B200_STAGED_EGC_FUSED_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALIGNN_FUSED_TILE_ROWS 128 /* in-edges (and destination nodes) per tile: the UMMA M */
+
+/* Segment-aligned tiling of the destination-sorted edge list: tile i covers whole in-edge segments of the nodes
+ * [v0, v0 + nseg) with rows <= 128 and nseg <= 128; descriptor = {v0, nseg, p0 = in_ptr[v0], rows}.
+ * tiles == NULL: count only.  Returns the number of tiles, -1 on bad arguments, -2 if a node has more than 128
+ * in-edges (the caller then keeps the two-kernel path). */
+int64_t alignn_b200_segment_tiles_host(const int32_t* in_ptr, int64_t num_nodes, int32_t* tiles, int64_t capacity);
+
+typedef struct {
+  size_t struct_size;
+  int64_t Nn, Ne;
+  int32_t d;            /* 32, 64, 128 or 256; the gate Linear is d x d */
+  int32_t norm_edges;   /* ALIGNN_NORM_STATS (train BatchNorm: M + column partials), ALIGNN_NORM_AFFINE (eval BatchNorm)
+                           or ALIGNN_NORM_LAYER (LayerNorm) */
+  int32_t residual;
+  float gate_eps, ln_eps;
+  const float* y;        /* [Ne,d] edge features = A operand of the gate GEMM */
+  const void* w_image;   /* alignn_b200_gemm_prepare_weights(W_eg, N=d, K=d) */
+  const float* bias;     /* [d] edge_gate.bias */
+  const float* P;        /* [Nn,4d] node projections [e_src | Bh | e_dst | src_update] */
+  const int32_t* src; const int32_t* dst;
+  const int32_t* in_ptr; const int32_t* in_eid;   /* in_eid NULL: edges already destination-sorted */
+  const int32_t* tiles; int32_t num_tiles;
+  const float* e_w; const float* e_b;             /* AFFINE: scale/shift; LAYER: gamma/beta */
+  float* M;         /* [Ne,d] or NULL (inference) */
+  float* y_out;     /* [Ne,d] or NULL; written for AFFINE / LAYER */
+  float* XP;        /* [Nn,d] x' = src_update(x) + h  (always) */
+  float* S; float* H; /* [Nn,d] or NULL (inference) */
+  float* partials;  /* STATS: [min(num_tiles,148)][2][d] = column sums of m and m^2 */
+  void* stream;
+} alignn_b200_egc_fused_fwd_args;
+
+int alignn_b200_egc_forward_fused(const alignn_b200_egc_fused_fwd_args* args);
+int alignn_b200_egc_fused_partial_rows(int32_t num_tiles);
+int alignn_b200_staged_last_cuda_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,226 @@
+"""Staged work (alignn_b200/csrc/staged): the one-kernel gate-GEMM + edge forward.
+
+CPU part (always runs): the segment-aligned tile packer, and a numpy emulation of the kernel's tile / row-phase /
+column-phase data flow driven by the packer's descriptors, against the oracle's formulas -- this pins the tiling
+semantics the CUDA kernel implements.
+GPU part: opt-in (ALIGNN_B200_STAGED=1) until the kernel has run on hardware once; it compares the fused kernel
+bit for bit with the shipped gemm_nt + egc_forward pair.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+from alignn_b200 import synthetic  # noqa: E402
+from alignn_b200.graph import Graph  # noqa: E402
+from oracle import golden_inputs as GI  # noqa: E402
+
+
+class FusedArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_size_t), ("Nn", C.c_int64), ("Ne", C.c_int64), ("d", C.c_int32),
+                ("norm_edges", C.c_int32), ("residual", C.c_int32), ("gate_eps", C.c_float), ("ln_eps", C.c_float),
+                ("y", C.c_void_p), ("w_image", C.c_void_p), ("bias", C.c_void_p), ("P", C.c_void_p),
+                ("src", C.c_void_p), ("dst", C.c_void_p), ("in_ptr", C.c_void_p), ("in_eid", C.c_void_p),
+                ("tiles", C.c_void_p), ("num_tiles", C.c_int32), ("e_w", C.c_void_p), ("e_b", C.c_void_p),
+                ("M", C.c_void_p), ("y_out", C.c_void_p), ("XP", C.c_void_p), ("S", C.c_void_p), ("H", C.c_void_p),
+                ("partials", C.c_void_p), ("stream", C.c_void_p)]
+
+
+@pytest.fixture(scope="module")
+def staged():
+    import build_staged
+    try:
+        path = build_staged.build()
+    except Exception as exc:  # no nvcc on this box and no prebuilt library
+        if os.path.exists(build_staged.LIB):
+            path = build_staged.LIB
+        else:
+            pytest.skip(f"staged library not built: {exc}")
+    lib = C.CDLL(path)
+    lib.alignn_b200_segment_tiles_host.restype = C.c_int64
+    lib.alignn_b200_segment_tiles_host.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+    lib.alignn_b200_egc_forward_fused.restype = C.c_int
+    lib.alignn_b200_egc_forward_fused.argtypes = [C.POINTER(FusedArgs)]
+    lib.alignn_b200_egc_fused_partial_rows.restype = C.c_int
+    lib.alignn_b200_egc_fused_partial_rows.argtypes = [C.c_int32]
+    return lib
+
+
+def pack_tiles(lib, in_ptr: np.ndarray):
+    in_ptr = np.ascontiguousarray(in_ptr, dtype=np.int32)
+    n = int(lib.alignn_b200_segment_tiles_host(in_ptr.ctypes.data, in_ptr.size - 1, None, 0))
+    if n < 0:
+        return n, None
+    tiles = np.zeros((max(n, 1), 4), dtype=np.int32)
+    assert lib.alignn_b200_segment_tiles_host(in_ptr.ctypes.data, in_ptr.size - 1, tiles.ctypes.data, n) == n
+    return n, tiles[:n]
+
+
+@pytest.mark.parametrize("degs", [[12] * 40, [0] * 300, [128, 1, 127, 0, 0, 128], [3, 0, 0, 125, 1, 1, 126] * 9,
+                                  list(range(0, 60)), []])
+def test_tile_packer_covers_every_segment_once(staged, degs):
+    in_ptr = np.concatenate([[0], np.cumsum(degs)]).astype(np.int32)
+    n, tiles = pack_tiles(staged, in_ptr)
+    assert n >= 0
+    v = 0
+    for v0, nseg, p0, rows in tiles:
+        assert v0 == v and 1 <= nseg <= 128 and 0 <= rows <= 128
+        assert p0 == in_ptr[v0] and rows == in_ptr[v0 + nseg] - in_ptr[v0]
+        v += nseg
+        if v < len(degs):      # greedy: the next segment did not fit
+            assert nseg == 128 or rows + degs[v] > 128
+    assert v == len(degs)
+
+
+def test_tile_packer_rejects_oversized_segment(staged):
+    in_ptr = np.array([0, 5, 134, 140], dtype=np.int32)
+    assert pack_tiles(staged, in_ptr)[0] == -2
+
+
+def _emulate(tiles, ix_in_ptr, in_eid, src, dst, y, W, b, P, eps=1e-6):
+    """numpy restatement of the kernel's data flow (fp64): per tile, rows = gathered y rows -> GEMM -> row phase ->
+    per-segment column sums -> S, H, x'."""
+    d = y.shape[1]
+    Nn = ix_in_ptr.size - 1
+    M = np.zeros_like(y)
+    S, H, XP = (np.zeros((Nn, d)) for _ in range(3))
+    stat = np.zeros((2, d))
+    for v0, nseg, p0, rows in tiles:
+        e = in_eid[p0:p0 + rows]
+        acc = y[e] @ W.T
+        m = (acc + b) + (P[src[e], 0:d] + P[dst[e], 2 * d:3 * d])
+        M[e] = m
+        sg = 1.0 / (1.0 + np.exp(-m))
+        sgc = sg * P[src[e], d:2 * d]
+        seg = ix_in_ptr[v0:v0 + nseg + 1] - p0
+        for j in range(nseg):
+            s1, s2 = sg[seg[j]:seg[j + 1]].sum(0), sgc[seg[j]:seg[j + 1]].sum(0)
+            h = s2 / (s1 + eps)
+            S[v0 + j], H[v0 + j], XP[v0 + j] = s1, h, P[v0 + j, 3 * d:] + h
+        stat[0] += m.sum(0)
+        stat[1] += (m * m).sum(0)
+    return M, S, H, XP, stat
+
+
+def test_tiled_dataflow_matches_oracle_formulas(staged):
+    from oracle import alignn_oracle as O
+    g, lg, _, _ = synthetic.make_batch(batch_size=3, atoms=7, k=12, seed=5, vary_atoms=True)
+    rng = np.random.default_rng(0)
+    for gr in (g, lg):
+        # shuffle the edge order so that in_eid is a real permutation
+        s, t = (a.numpy() for a in gr.edges())
+        perm = rng.permutation(s.size)
+        gr2 = Graph(s[perm], t[perm], gr.num_nodes())
+        ix = gr2.index
+        d = 32
+        conv = O.EdgeGatedGraphConv(d, d, norm="batchnorm").double()
+        GI.fill_state_dict(conv, 9)
+        x, y = GI.features(2, gr2.num_nodes(), d).double(), GI.features(3, gr2.num_edges(), d).double()
+        Wcat = torch.cat([conv.src_gate.weight, conv.dst_update.weight, conv.dst_gate.weight, conv.src_update.weight])
+        bcat = torch.cat([conv.src_gate.bias, conv.dst_update.bias, conv.dst_gate.bias, conv.src_update.bias])
+        P = (x @ Wcat.T + bcat).detach().numpy()
+        n, tiles = pack_tiles(staged, ix.in_ptr.numpy())
+        assert n > 0
+        M, S, H, XP, stat = _emulate(tiles, ix.in_ptr.numpy(), ix.in_eid.numpy().astype(np.int64),
+                                     ix.src.numpy().astype(np.int64), ix.dst.numpy().astype(np.int64), y.numpy(),
+                                     conv.edge_gate.weight.detach().numpy(), conv.edge_gate.bias.detach().numpy(), P)
+        # the reference's intermediate quantities (alignn.py:98-110) by plain index_add
+        src, dst = (a.long() for a in gr2.edges())
+        with torch.no_grad():
+            e_src = x @ conv.src_gate.weight.T + conv.src_gate.bias
+            Bh = x @ conv.dst_update.weight.T + conv.dst_update.bias
+            e_dst = x @ conv.dst_gate.weight.T + conv.dst_gate.bias
+            m = e_src[src] + e_dst[dst] + y @ conv.edge_gate.weight.T + conv.edge_gate.bias
+            sig = torch.sigmoid(m)
+            Sref = torch.zeros(gr2.num_nodes(), d, dtype=torch.float64).index_add_(0, dst, sig)
+            Shref = torch.zeros(gr2.num_nodes(), d, dtype=torch.float64).index_add_(0, dst, sig * Bh[src])
+            href = Shref / (Sref + 1e-6)
+            xpref = x @ conv.src_update.weight.T + conv.src_update.bias + href
+        np.testing.assert_allclose(M, m.numpy(), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(S, Sref.numpy(), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(H, href.numpy(), rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(XP, xpref.numpy(), rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(stat[0], m.sum(0).numpy(), rtol=1e-10, atol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------------ GPU (opt-in)
+needs_optin = pytest.mark.skipif(os.environ.get("ALIGNN_B200_STAGED") != "1",
+                                 reason="staged kernel: opt in with ALIGNN_B200_STAGED=1 (not yet validated on hardware)")
+
+
+def _run_fused(lib, gr, x, y, conv_w, norm_edges, d, train, e_w=None, e_b=None, residual=True):
+    """Returns the fused kernel's outputs and the shipped two-kernel path's, on the same inputs."""
+    from alignn_b200 import ops
+    from alignn_b200._lib import ptr, stream_ptr
+    dev = x.device
+    ix = gr.index
+    Wcat, bcat, W_eg, b_eg = conv_w
+    P = ops.gemm_nt(x, ops.WeightImage(Wcat), bcat)
+    img = ops.WeightImage(W_eg)
+    n, tiles = pack_tiles(lib, ix.in_ptr.cpu().numpy())
+    assert n > 0
+    tiles_d = torch.from_numpy(tiles).to(dev)
+    Nn, Ne = x.shape[0], y.shape[0]
+    new = lambda *s: torch.full(s, float("nan"), device=dev, dtype=torch.float32)  # noqa: E731
+    rows = lib.alignn_b200_egc_fused_partial_rows(n)
+    out = dict(M=new(Ne, d) if train else None, XP=new(Nn, d), S=new(Nn, d) if train else None,
+               H=new(Nn, d) if train else None, partials=new(rows, 2, d) if norm_edges == ops.NORM_STATS else None,
+               y_out=new(Ne, d) if norm_edges != ops.NORM_STATS else None)
+    a = FusedArgs(struct_size=C.sizeof(FusedArgs), Nn=Nn, Ne=Ne, d=d, norm_edges=norm_edges, residual=int(residual),
+                  gate_eps=1e-6, ln_eps=1e-5, y=ptr(y), w_image=ops.ptr_any(img.buf), bias=ptr(b_eg), P=ptr(P),
+                  src=ptr(ix.src), dst=ptr(ix.dst), in_ptr=ptr(ix.in_ptr), in_eid=None if ix.dst_sorted else ptr(ix.in_eid),
+                  tiles=ptr(tiles_d), num_tiles=n, e_w=ptr(e_w), e_b=ptr(e_b), M=ptr(out["M"]), y_out=ptr(out["y_out"]),
+                  XP=ptr(out["XP"]), S=ptr(out["S"]), H=ptr(out["H"]), partials=ptr(out["partials"]), stream=stream_ptr())
+    rc = lib.alignn_b200_egc_forward_fused(C.byref(a))
+    assert rc == 0, rc
+    torch.cuda.synchronize()
+    G = ops.gemm_nt(y, img, b_eg)
+    zeros = torch.zeros(d, device=dev)
+    ref = ops.egc_forward(ix, x, y, G, P, zeros + 1, zeros, e_w if e_w is not None else zeros + 1,
+                          e_b if e_b is not None else zeros, norm_nodes=ops.NORM_STATS if train else ops.NORM_AFFINE,
+                          norm_edges=norm_edges, residual=residual, save=True, need_edge_out=True)
+    torch.cuda.synchronize()
+    return out, ref
+
+
+@pytest.mark.gpu
+@needs_optin
+@pytest.mark.parametrize("d", [256, 64])
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_fused_forward_bit_identical_to_shipped_path(staged, d, shuffle):
+    from alignn_b200 import ops
+    dev = torch.device("cuda:0")
+    g, lg, _, _ = synthetic.make_batch(batch_size=4, atoms=9, k=12, seed=17, vary_atoms=True)
+    for gr in (g, lg):
+        if shuffle:
+            s, t = (a.numpy() for a in gr.edges())
+            perm = np.random.default_rng(1).permutation(s.size)
+            gr = Graph(s[perm], t[perm], gr.num_nodes())
+        grd = gr.to(dev)
+        x, y = GI.features(2, gr.num_nodes(), d).to(dev), GI.features(3, gr.num_edges(), d).to(dev)
+        gen = torch.Generator().manual_seed(3)
+        Wcat = (torch.randn(4 * d, d, generator=gen) / d ** 0.5).to(dev)
+        W_eg = (torch.randn(d, d, generator=gen) / d ** 0.5).to(dev)
+        bcat, b_eg = torch.randn(4 * d, generator=gen).to(dev), torch.randn(d, generator=gen).to(dev)
+        e_w, e_b = (torch.rand(d, generator=gen) + 0.5).to(dev), torch.randn(d, generator=gen).to(dev)
+        # training BatchNorm: M, S, H, x' bit-identical; column sums to fp32 round-off
+        out, ref = _run_fused(staged, grd, x, y, (Wcat, bcat, W_eg, b_eg), ops.NORM_STATS, d, True)
+        for k in ("M", "S", "H", "XP"):
+            assert torch.equal(out[k], ref[k]), k
+        sums = out["partials"].double().sum(0)
+        refs = ref["partials"].double().sum(0)[:2]
+        assert torch.allclose(sums, refs, rtol=1e-5, atol=1e-3)
+        # eval BatchNorm: y_out bit-identical; LayerNorm: the row statistics are summed in a different order
+        out, ref = _run_fused(staged, grd, x, y, (Wcat, bcat, W_eg, b_eg), ops.NORM_AFFINE, d, False, e_w, e_b)
+        assert torch.equal(out["y_out"], ref["y_out"])
+        assert torch.equal(out["XP"], ref["XP"])
+        out, ref = _run_fused(staged, grd, x, y, (Wcat, bcat, W_eg, b_eg), ops.NORM_LAYER, d, True, e_w, e_b)
+        assert torch.equal(out["M"], ref["M"])
+        err = (out["y_out"] - ref["y_out"]).abs().max().item()
+        assert err <= 1e-5 * max(ref["y_out"].abs().max().item(), 1.0), err
