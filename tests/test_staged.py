@@ -6,7 +6,6 @@ semantics the CUDA kernel implements.
 GPU part: opt-in (ALIGNN_B200_STAGED=1) until the kernel has run on hardware once; it compares the fused kernel
 bit for bit with the shipped gemm_nt + egc_forward pair.
 """
-import ctypes as C
 import os
 import sys
 
@@ -22,44 +21,18 @@ from alignn_b200.graph import Graph  # noqa: E402
 from oracle import golden_inputs as GI  # noqa: E402
 
 
-class FusedArgs(C.Structure):
-    _fields_ = [("struct_size", C.c_size_t), ("Nn", C.c_int64), ("Ne", C.c_int64), ("d", C.c_int32),
-                ("norm_edges", C.c_int32), ("residual", C.c_int32), ("gate_eps", C.c_float), ("ln_eps", C.c_float),
-                ("y", C.c_void_p), ("w_image", C.c_void_p), ("bias", C.c_void_p), ("P", C.c_void_p),
-                ("src", C.c_void_p), ("dst", C.c_void_p), ("in_ptr", C.c_void_p), ("in_eid", C.c_void_p),
-                ("tiles", C.c_void_p), ("num_tiles", C.c_int32), ("e_w", C.c_void_p), ("e_b", C.c_void_p),
-                ("M", C.c_void_p), ("y_out", C.c_void_p), ("XP", C.c_void_p), ("S", C.c_void_p), ("H", C.c_void_p),
-                ("partials", C.c_void_p), ("stream", C.c_void_p)]
-
-
 @pytest.fixture(scope="module")
 def staged():
-    import build_staged
+    import staged_binding
     try:
-        path = build_staged.build()
+        return staged_binding.load()
     except Exception as exc:  # no nvcc on this box and no prebuilt library
-        if os.path.exists(build_staged.LIB):
-            path = build_staged.LIB
-        else:
-            pytest.skip(f"staged library not built: {exc}")
-    lib = C.CDLL(path)
-    lib.alignn_b200_segment_tiles_host.restype = C.c_int64
-    lib.alignn_b200_segment_tiles_host.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
-    lib.alignn_b200_egc_forward_fused.restype = C.c_int
-    lib.alignn_b200_egc_forward_fused.argtypes = [C.POINTER(FusedArgs)]
-    lib.alignn_b200_egc_fused_partial_rows.restype = C.c_int
-    lib.alignn_b200_egc_fused_partial_rows.argtypes = [C.c_int32]
-    return lib
+        pytest.skip(f"staged library not built: {exc}")
 
 
-def pack_tiles(lib, in_ptr: np.ndarray):
-    in_ptr = np.ascontiguousarray(in_ptr, dtype=np.int32)
-    n = int(lib.alignn_b200_segment_tiles_host(in_ptr.ctypes.data, in_ptr.size - 1, None, 0))
-    if n < 0:
-        return n, None
-    tiles = np.zeros((max(n, 1), 4), dtype=np.int32)
-    assert lib.alignn_b200_segment_tiles_host(in_ptr.ctypes.data, in_ptr.size - 1, tiles.ctypes.data, n) == n
-    return n, tiles[:n]
+def pack_tiles(lib, in_ptr):
+    import staged_binding
+    return staged_binding.pack_tiles(lib, in_ptr)
 
 
 @pytest.mark.parametrize("degs", [[12] * 40, [0] * 300, [128, 1, 127, 0, 0, 128], [3, 0, 0, 125, 1, 1, 126] * 9,
@@ -156,8 +129,8 @@ needs_optin = pytest.mark.skipif(os.environ.get("ALIGNN_B200_STAGED") != "1",
 
 def _run_fused(lib, gr, x, y, conv_w, norm_edges, d, train, e_w=None, e_b=None, residual=True):
     """Returns the fused kernel's outputs and the shipped two-kernel path's, on the same inputs."""
+    import staged_binding
     from alignn_b200 import ops
-    from alignn_b200._lib import ptr, stream_ptr
     dev = x.device
     ix = gr.index
     Wcat, bcat, W_eg, b_eg = conv_w
@@ -166,19 +139,7 @@ def _run_fused(lib, gr, x, y, conv_w, norm_edges, d, train, e_w=None, e_b=None, 
     n, tiles = pack_tiles(lib, ix.in_ptr.cpu().numpy())
     assert n > 0
     tiles_d = torch.from_numpy(tiles).to(dev)
-    Nn, Ne = x.shape[0], y.shape[0]
-    new = lambda *s: torch.full(s, float("nan"), device=dev, dtype=torch.float32)  # noqa: E731
-    rows = lib.alignn_b200_egc_fused_partial_rows(n)
-    out = dict(M=new(Ne, d) if train else None, XP=new(Nn, d), S=new(Nn, d) if train else None,
-               H=new(Nn, d) if train else None, partials=new(rows, 2, d) if norm_edges == ops.NORM_STATS else None,
-               y_out=new(Ne, d) if norm_edges != ops.NORM_STATS else None)
-    a = FusedArgs(struct_size=C.sizeof(FusedArgs), Nn=Nn, Ne=Ne, d=d, norm_edges=norm_edges, residual=int(residual),
-                  gate_eps=1e-6, ln_eps=1e-5, y=ptr(y), w_image=ops.ptr_any(img.buf), bias=ptr(b_eg), P=ptr(P),
-                  src=ptr(ix.src), dst=ptr(ix.dst), in_ptr=ptr(ix.in_ptr), in_eid=None if ix.dst_sorted else ptr(ix.in_eid),
-                  tiles=ptr(tiles_d), num_tiles=n, e_w=ptr(e_w), e_b=ptr(e_b), M=ptr(out["M"]), y_out=ptr(out["y_out"]),
-                  XP=ptr(out["XP"]), S=ptr(out["S"]), H=ptr(out["H"]), partials=ptr(out["partials"]), stream=stream_ptr())
-    rc = lib.alignn_b200_egc_forward_fused(C.byref(a))
-    assert rc == 0, rc
+    out = staged_binding.fused_forward(lib, ix, tiles_d, n, y, img, b_eg, P, norm_edges, train, e_w, e_b, residual)
     torch.cuda.synchronize()
     G = ops.gemm_nt(y, img, b_eg)
     zeros = torch.zeros(d, device=dev)

@@ -1,0 +1,75 @@
+"""ctypes binding of the staged library (alignn_b200/csrc/staged/egc_fused.h), shared by tests/test_staged.py and
+tools/bench_fused.py.  Not part of the product: the shipped binding is alignn_b200/_lib.py."""
+import ctypes as C
+import os
+
+import numpy as np
+
+import build_staged
+
+
+class FusedArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_size_t), ("Nn", C.c_int64), ("Ne", C.c_int64), ("d", C.c_int32),
+                ("norm_edges", C.c_int32), ("residual", C.c_int32), ("gate_eps", C.c_float), ("ln_eps", C.c_float),
+                ("y", C.c_void_p), ("w_image", C.c_void_p), ("bias", C.c_void_p), ("P", C.c_void_p),
+                ("src", C.c_void_p), ("dst", C.c_void_p), ("in_ptr", C.c_void_p), ("in_eid", C.c_void_p),
+                ("tiles", C.c_void_p), ("num_tiles", C.c_int32), ("e_w", C.c_void_p), ("e_b", C.c_void_p),
+                ("M", C.c_void_p), ("y_out", C.c_void_p), ("XP", C.c_void_p), ("S", C.c_void_p), ("H", C.c_void_p),
+                ("partials", C.c_void_p), ("stream", C.c_void_p)]
+
+
+def load():
+    """Build if stale (needs nvcc) or fall back to the prebuilt .so that travelled with the tree."""
+    try:
+        path = build_staged.build()
+    except Exception:
+        if not os.path.exists(build_staged.LIB):
+            raise
+        path = build_staged.LIB
+    lib = C.CDLL(path)
+    lib.alignn_b200_segment_tiles_host.restype = C.c_int64
+    lib.alignn_b200_segment_tiles_host.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+    lib.alignn_b200_egc_forward_fused.restype = C.c_int
+    lib.alignn_b200_egc_forward_fused.argtypes = [C.POINTER(FusedArgs)]
+    lib.alignn_b200_egc_fused_partial_rows.restype = C.c_int
+    lib.alignn_b200_egc_fused_partial_rows.argtypes = [C.c_int32]
+    lib.alignn_b200_staged_last_cuda_error.restype = C.c_int
+    return lib
+
+
+def pack_tiles(lib, in_ptr: np.ndarray):
+    """(num_tiles, int32 [num_tiles,4] descriptors {v0, nseg, p0, rows}); num_tiles < 0 on failure (-2: a node has
+    more than 128 in-edges)."""
+    in_ptr = np.ascontiguousarray(in_ptr, dtype=np.int32)
+    n = int(lib.alignn_b200_segment_tiles_host(in_ptr.ctypes.data, in_ptr.size - 1, None, 0))
+    if n < 0:
+        return n, None
+    tiles = np.zeros((max(n, 1), 4), dtype=np.int32)
+    assert lib.alignn_b200_segment_tiles_host(in_ptr.ctypes.data, in_ptr.size - 1, tiles.ctypes.data, n) == n
+    return n, tiles[:n]
+
+
+def fused_forward(lib, ix, tiles_d, n_tiles, y, img, b_eg, P, norm_edges, train, e_w=None, e_b=None, residual=True,
+                  out=None):
+    """Launch the fused kernel on torch's current stream.  `out` (a dict from a previous call) is reused if given."""
+    import torch
+    from alignn_b200 import ops
+    from alignn_b200._lib import ptr, stream_ptr
+    dev = y.device if y.numel() else P.device
+    Nn, d = P.shape[0], P.shape[1] // 4
+    Ne = y.shape[0]
+    if out is None:
+        new = lambda *s: torch.full(s, float("nan"), device=dev, dtype=torch.float32)  # noqa: E731
+        rows = lib.alignn_b200_egc_fused_partial_rows(n_tiles)
+        out = dict(M=new(Ne, d) if train else None, XP=new(Nn, d), S=new(Nn, d) if train else None,
+                   H=new(Nn, d) if train else None, partials=new(rows, 2, d) if norm_edges == ops.NORM_STATS else None,
+                   y_out=new(Ne, d) if norm_edges != ops.NORM_STATS else None)
+    a = FusedArgs(struct_size=C.sizeof(FusedArgs), Nn=Nn, Ne=Ne, d=d, norm_edges=norm_edges, residual=int(residual),
+                  gate_eps=1e-6, ln_eps=1e-5, y=ptr(y), w_image=ops.ptr_any(img.buf), bias=ptr(b_eg), P=ptr(P),
+                  src=ptr(ix.src), dst=ptr(ix.dst), in_ptr=ptr(ix.in_ptr), in_eid=None if ix.dst_sorted else ptr(ix.in_eid),
+                  tiles=ptr(tiles_d), num_tiles=n_tiles, e_w=ptr(e_w), e_b=ptr(e_b), M=ptr(out["M"]), y_out=ptr(out["y_out"]),
+                  XP=ptr(out["XP"]), S=ptr(out["S"]), H=ptr(out["H"]), partials=ptr(out["partials"]), stream=stream_ptr())
+    rc = lib.alignn_b200_egc_forward_fused(C.byref(a))
+    if rc != 0:
+        raise RuntimeError(f"alignn_b200_egc_forward_fused -> {rc} (cuda error {lib.alignn_b200_staged_last_cuda_error()})")
+    return out
