@@ -50,6 +50,12 @@ typedef struct {
 
 int alignn_b200_egc_forward_fused(const alignn_b200_egc_fused_fwd_args* args);
 int alignn_b200_egc_fused_partial_rows(int32_t num_tiles);
+
+/* Node tail for LayerNorm models after the fused kernel: out = (res ? res : 0) + silu(LayerNorm(R) * gamma + beta),
+ * rows [n,d] (alignn_atomwise.py:209-211 applied to x' = XP).  BatchNorm models use the shipped
+ * rowstats_partials / bn_finalize / affine_silu_residual entry points on XP instead. */
+int alignn_b200_ln_silu_residual(const float* R, const float* res, const float* gamma, const float* beta, float eps,
+                                 float* out, int64_t n, int d, void* stream);
 int alignn_b200_staged_last_cuda_error(void);
 
 #ifdef __cplusplus

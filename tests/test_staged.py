@@ -185,3 +185,48 @@ def test_fused_forward_bit_identical_to_shipped_path(staged, d, shuffle):
         assert torch.equal(out["M"], ref["M"])
         err = (out["y_out"] - ref["y_out"]).abs().max().item()
         assert err <= 1e-5 * max(ref["y_out"].abs().max().item(), 1.0), err
+
+
+@pytest.mark.gpu
+@needs_optin
+@pytest.mark.parametrize("mode", ["layernorm", "bn_eval", "bn_train"])
+def test_fused_conv_forward_matches_shipped_forward(staged, mode):
+    """Fused kernel + node tail against `ops.egc_forward` (+ the BatchNorm finalize/apply steps) end to end."""
+    import staged_binding
+    from alignn_b200 import ops
+    dev = torch.device("cuda:0")
+    d = 128
+    g, lg, _, _ = synthetic.make_batch(batch_size=5, atoms=8, k=12, seed=23, vary_atoms=True)
+    for gr in (g, lg):
+        grd = gr.to(dev)
+        ix = grd.index
+        Nn, Ne = gr.num_nodes(), gr.num_edges()
+        x, y = GI.features(2, Nn, d).to(dev), GI.features(3, Ne, d).to(dev)
+        gen = torch.Generator().manual_seed(5)
+        Wcat = (torch.randn(4 * d, d, generator=gen) / d ** 0.5).to(dev)
+        W_eg = (torch.randn(d, d, generator=gen) / d ** 0.5).to(dev)
+        bcat, b_eg = torch.randn(4 * d, generator=gen).to(dev), torch.randn(d, generator=gen).to(dev)
+        n_w, n_b, e_w, e_b = ((torch.rand(d, generator=gen) + 0.5).to(dev) for _ in range(4))
+        P = ops.gemm_nt(x, ops.WeightImage(Wcat), bcat)
+        img = ops.WeightImage(W_eg)
+        G = ops.gemm_nt(y, img, b_eg)
+        n, tiles = pack_tiles(staged, ix.in_ptr.cpu().numpy())
+        tiles_d = torch.from_numpy(tiles).to(dev)
+        norm = {"layernorm": ops.NORM_LAYER, "bn_eval": ops.NORM_AFFINE, "bn_train": ops.NORM_STATS}[mode]
+        kw = dict(norm_nodes=norm, norm_edges=norm, residual=True, save=True, need_edge_out=True)
+        ref = ops.egc_forward(ix, x, y, G, P, n_w, n_b, e_w, e_b, **kw)
+        out = staged_binding.conv_forward_like(staged, ix, tiles_d, n, x, y, img, b_eg, P, n_w, n_b, e_w, e_b, **kw)
+        torch.cuda.synchronize()
+        for k in ("M", "XP", "S", "H"):
+            assert torch.equal(out[k], ref[k]), (mode, k)
+        if mode == "bn_train":
+            for which, cnt, part, R, res in ((1, Nn, out["partials_n"], out["XP"], x), (0, Ne, out["partials_e"], out["M"], y)):
+                a = ops.bn_finalize(ref["partials"], which, cnt, n_w, n_b, 1e-5, 0.1, None, None)
+                b = ops.bn_finalize(part, 0, cnt, n_w, n_b, 1e-5, 0.1, None, None)
+                for u, v in zip(a, b):
+                    assert torch.allclose(u, v, rtol=1e-5, atol=1e-6)
+        else:
+            tol = 0.0 if mode == "bn_eval" else 1e-5
+            for k in ("x_out", "y_out"):
+                err = (out[k] - ref[k]).abs().max().item()
+                assert err <= tol * max(ref[k].abs().max().item(), 1.0), (mode, k, err)

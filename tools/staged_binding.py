@@ -50,7 +50,7 @@ def pack_tiles(lib, in_ptr: np.ndarray):
 
 
 def fused_forward(lib, ix, tiles_d, n_tiles, y, img, b_eg, P, norm_edges, train, e_w=None, e_b=None, residual=True,
-                  out=None):
+                  out=None, need_edge_out=True):
     """Launch the fused kernel on torch's current stream.  `out` (a dict from a previous call) is reused if given."""
     import torch
     from alignn_b200 import ops
@@ -63,7 +63,7 @@ def fused_forward(lib, ix, tiles_d, n_tiles, y, img, b_eg, P, norm_edges, train,
         rows = lib.alignn_b200_egc_fused_partial_rows(n_tiles)
         out = dict(M=new(Ne, d) if train else None, XP=new(Nn, d), S=new(Nn, d) if train else None,
                    H=new(Nn, d) if train else None, partials=new(rows, 2, d) if norm_edges == ops.NORM_STATS else None,
-                   y_out=new(Ne, d) if norm_edges != ops.NORM_STATS else None)
+                   y_out=new(Ne, d) if (norm_edges != ops.NORM_STATS and need_edge_out) else None)
     a = FusedArgs(struct_size=C.sizeof(FusedArgs), Nn=Nn, Ne=Ne, d=d, norm_edges=norm_edges, residual=int(residual),
                   gate_eps=1e-6, ln_eps=1e-5, y=ptr(y), w_image=ops.ptr_any(img.buf), bias=ptr(b_eg), P=ptr(P),
                   src=ptr(ix.src), dst=ptr(ix.dst), in_ptr=ptr(ix.in_ptr), in_eid=None if ix.dst_sorted else ptr(ix.in_eid),
@@ -72,4 +72,41 @@ def fused_forward(lib, ix, tiles_d, n_tiles, y, img, b_eg, P, norm_edges, train,
     rc = lib.alignn_b200_egc_forward_fused(C.byref(a))
     if rc != 0:
         raise RuntimeError(f"alignn_b200_egc_forward_fused -> {rc} (cuda error {lib.alignn_b200_staged_last_cuda_error()})")
+    return out
+
+
+def conv_forward_like(lib, ix, tiles_d, n_tiles, x, y, img, b_eg, P, n_w, n_b, e_w, e_b, *, norm_nodes, norm_edges,
+                      residual=True, save=True, need_edge_out=True):
+    """The whole post-Linear forward of one conv built from the fused kernel + node tail, with the output contract of
+    `alignn_b200.ops.egc_forward` (x_out / y_out are None in STATS mode; partials_e / partials_n then feed
+    `ops.bn_finalize(..., which=0, ...)`).  This is what conv.py will call once the kernel is validated."""
+    import torch
+    from alignn_b200 import _lib, ops
+    from alignn_b200._lib import ptr, stream_ptr
+    main = _lib.load()
+    Nn, d = x.shape
+    stats = norm_nodes == ops.NORM_STATS or norm_edges == ops.NORM_STATS
+    train = save or stats
+    out = fused_forward(lib, ix, tiles_d, n_tiles, y, img, b_eg, P, norm_edges, train, e_w, e_b, residual,
+                        need_edge_out=need_edge_out)
+    out["partials_e"] = out.pop("partials")
+    out["partials_n"] = None
+    out["x_out"] = None
+    XP = out["XP"]
+    if norm_nodes == ops.NORM_STATS:
+        rows = ops.partial_rows(Nn, d)
+        part = torch.empty(rows, 2, d, device=x.device, dtype=torch.float32)
+        _lib.check(main.alignn_b200_rowstats_partials(ptr(XP), Nn, d, ptr(part), rows, stream_ptr()), "rowstats_partials")
+        out["partials_n"] = part
+    elif norm_nodes == ops.NORM_AFFINE:
+        out["x_out"] = ops.affine_silu_residual(XP, x if residual else None, n_w, n_b)
+    else:
+        xo = torch.empty_like(XP)
+        lib.alignn_b200_ln_silu_residual.restype = C.c_int
+        lib.alignn_b200_ln_silu_residual.argtypes = [C.c_void_p] * 4 + [C.c_float, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+        rc = lib.alignn_b200_ln_silu_residual(ptr(XP), ptr(x) if residual else None, ptr(n_w), ptr(n_b), 1e-5, ptr(xo), Nn, d,
+                                              stream_ptr())
+        if rc != 0:
+            raise RuntimeError(f"alignn_b200_ln_silu_residual -> {rc}")
+        out["x_out"] = xo
     return out
