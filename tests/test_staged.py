@@ -230,3 +230,58 @@ def test_fused_conv_forward_matches_shipped_forward(staged, mode):
             for k in ("x_out", "y_out"):
                 err = (out[k] - ref[k]).abs().max().item()
                 assert err <= tol * max(ref[k].abs().max().item(), 1.0), (mode, k, err)
+
+
+# ---- device-side structure builders and force reductions (graph_device.cu) -----------------------------------------
+def _test_graphs():
+    g, lg, _, _ = synthetic.make_batch(batch_size=3, atoms=6, k=12, seed=31, vary_atoms=True)
+    s, t = (a.numpy() for a in g.edges())
+    perm = np.random.default_rng(2).permutation(s.size)
+    shuffled = Graph(s[perm], t[perm], g.num_nodes(), g.batch_num_nodes(), g.batch_num_edges())
+    loops = Graph(np.array([0, 1, 1, 2, 2, 2, 0]), np.array([1, 1, 0, 2, 0, 2, 0]), 4)      # self-loops, isolated node 3
+    empty = Graph(np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), 3)
+    return [g, lg, shuffled, loops, empty]
+
+
+@pytest.mark.gpu
+@needs_optin
+def test_device_csr_and_line_graph_bit_identical_to_host_builders(staged):
+    import staged_binding
+    dev = torch.device("cuda:0")
+    for gr in _test_graphs():
+        ix = gr.index                                   # built by the native host builder
+        src, dst = ix.src.to(dev), ix.dst.to(dev)
+        out = staged_binding.csr_build_device(staged, src, dst, gr.num_nodes())
+        for k in ("in_ptr", "in_eid", "out_ptr", "out_eid"):
+            assert torch.equal(out[k].cpu(), getattr(ix, k)), k
+        assert out["dst_sorted"] == ix.dst_sorted and out["max_in_deg"] == ix.max_in_deg
+        lsrc, ldst, off = staged_binding.line_graph_device(staged, src, dst, out["in_ptr"], out["in_eid"])
+        ref = gr.line_graph()
+        rs, rt = ref.edges()
+        assert torch.equal(lsrc.cpu().long(), rs.long()) and torch.equal(ldst.cpu().long(), rt.long())
+        assert torch.equal(off.cpu(), ref.index.in_ptr)
+
+
+@pytest.mark.gpu
+@needs_optin
+def test_device_force_scatter_and_virial_match_fp64(staged):
+    import staged_binding
+    from oracle import alignn_oracle as O
+    from helpers import to_oracle
+    dev = torch.device("cuda:0")
+    g, _, _, _ = synthetic.make_batch(batch_size=3, atoms=7, k=12, seed=37, vary_atoms=True)
+    E = g.num_edges()
+    pf = GI.features(8, E, 3)
+    ix = g.to(dev).index
+    f = staged_binding.pair_force_scatter(staged, pf.to(dev), ix).cpu().double()
+    s, t = (a.long() for a in g.edges())
+    zeros = torch.zeros(g.num_nodes(), 3, dtype=torch.float64)
+    ref = zeros.index_add(0, t, pf.double()) - zeros.index_add(0, s, pf.double())
+    assert (f - ref).abs().max() <= 1e-5 * ref.abs().max()
+    vols = GI.cell_volumes(g.batch_num_nodes())
+    eoff = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(g.batch_num_edges().long(), 0)]).to(dev)
+    noff = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(g.batch_num_nodes().long(), 0)]).to(dev)
+    st = staged_binding.virial_stress(staged, g.edata["r"].to(dev), pf.to(dev), eoff, noff, vols.to(dev), 10.0).cpu().double()
+    og = to_oracle(g, torch.float64)
+    ref = O.virial_stress(og, pf.double(), vols.double(), stress_multiplier=10.0)
+    assert (st - ref).abs().max() <= 1e-5 * ref.abs().max()
