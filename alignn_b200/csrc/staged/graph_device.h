@@ -31,6 +31,20 @@ int alignn_b200_line_graph_offsets(const int32_t* src, const int32_t* dst, const
 int alignn_b200_line_graph_fill(const int32_t* src, const int32_t* dst, const int32_t* in_ptr, const int32_t* in_eid,
                                 int64_t num_edges, const int32_t* offsets, int32_t* lsrc, int32_t* ldst, void* stream);
 
+/* Periodic radius graph on the device = alignn_b200_radius_graph_{count,build}_host (alignn/graphs.py:267-364): bonds
+ * u -> v for every image `c` of v with atol < |x_v + shifts[c] - x_u| <= cutoff, in (u, c, v) order, double precision
+ * with the host builder's operation order (bit-identical bond list and displacement vectors).  offsets[u] = first bond
+ * of atom u, offsets[N] = number of bonds (read it back to size the outputs); fill with empty outputs is an error only
+ * if bonds exist.  The caller computes `shifts = cells @ lattice` and handles the cutoff-growth retry
+ * (graphs.py:347-350) exactly as alignn_b200.neighbors.radius_graph does for the host scan. */
+size_t alignn_b200_radius_graph_workspace_bytes(int64_t num_atoms);
+int alignn_b200_radius_graph_offsets(const double* cart_coords, const double* shifts, int64_t num_atoms, int64_t num_images,
+                                     double cutoff, double atol, int32_t* offsets, void* workspace, size_t workspace_bytes,
+                                     void* stream);
+int alignn_b200_radius_graph_fill(const double* cart_coords, const double* shifts, int64_t num_atoms, int64_t num_images,
+                                  double cutoff, double atol, const int32_t* offsets, int32_t* u, int32_t* v,
+                                  int32_t* image_index, float* r, void* stream);
+
 /* forces[v] = sum over in-edges of pair_forces - (add_reverse ? sum over out-edges : 0)   (alignn_atomwise.py:547-563:
  * update_all(copy_e, sum) on g and on dgl.reverse(g)); pair_forces [E,3], forces [Nn,3].  in_eid NULL = identity. */
 int alignn_b200_pair_force_scatter(const float* pair_forces, const int32_t* in_ptr, const int32_t* in_eid,

@@ -285,3 +285,29 @@ def test_device_force_scatter_and_virial_match_fp64(staged):
     og = to_oracle(g, torch.float64)
     ref = O.virial_stress(og, pf.double(), vols.double(), stress_multiplier=10.0)
     assert (st - ref).abs().max() <= 1e-5 * ref.abs().max()
+
+
+@pytest.mark.gpu
+@needs_optin
+@pytest.mark.parametrize("reps,jitter", [(1, 0.0), (2, 0.05), (3, 0.1)])
+def test_device_radius_scan_bit_identical_to_host_scan(staged, reps, jitter):
+    """Same bonds, same order, same float32 displacement vectors as the native host scan (graphs.py:267-364)."""
+    import math
+    import staged_binding
+    from alignn_b200 import neighbors
+    dev = torch.device("cuda:0")
+    lat, X = neighbors.diamond_supercell(reps=reps, jitter=jitter, seed=4)
+    cutoff = 4.0
+    u, v, r, cells_of_bond = neighbors.radius_graph(lat, X, cutoff=cutoff)
+    # the image enumeration of neighbors.radius_graph (graphs.py:291-303)
+    frac = X @ np.linalg.inv(lat)
+    recp_len = np.sqrt(((2 * math.pi * np.linalg.inv(lat).T) ** 2).sum(1))
+    maxr = np.ceil((cutoff + 0.5) * recp_len / (2 * math.pi))
+    nmin, nmax = np.floor(frac.min(0)) - maxr, np.ceil(frac.max(0)) + maxr
+    cells = np.stack(np.meshgrid(*[np.arange(a, b, dtype=np.float64) for a, b in zip(nmin, nmax)], indexing="ij"), -1).reshape(-1, 3)
+    shifts = np.ascontiguousarray(cells @ lat)
+    du, dv, dc, dr = staged_binding.radius_scan_device(staged, torch.from_numpy(np.ascontiguousarray(X)).to(dev),
+                                                       torch.from_numpy(shifts).to(dev), cutoff)
+    assert np.array_equal(du.cpu().numpy(), u) and np.array_equal(dv.cpu().numpy(), v)
+    assert np.array_equal(cells[dc.cpu().numpy()], cells_of_bond)
+    assert np.array_equal(dr.cpu().numpy(), r)

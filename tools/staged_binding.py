@@ -125,6 +125,12 @@ def _sig(lib):
     lib.alignn_b200_line_graph_offsets.argtypes = [vp, vp, vp, i64, vp, vp, sz, vp]
     lib.alignn_b200_line_graph_fill.restype = i32
     lib.alignn_b200_line_graph_fill.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp]
+    lib.alignn_b200_radius_graph_workspace_bytes.restype = sz
+    lib.alignn_b200_radius_graph_workspace_bytes.argtypes = [i64]
+    lib.alignn_b200_radius_graph_offsets.restype = i32
+    lib.alignn_b200_radius_graph_offsets.argtypes = [vp, vp, i64, i64, C.c_double, C.c_double, vp, vp, sz, vp]
+    lib.alignn_b200_radius_graph_fill.restype = i32
+    lib.alignn_b200_radius_graph_fill.argtypes = [vp, vp, i64, i64, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]
     lib.alignn_b200_pair_force_scatter.restype = i32
     lib.alignn_b200_pair_force_scatter.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp]
     lib.alignn_b200_virial_stress.restype = i32
@@ -196,3 +202,26 @@ def virial_stress(lib, r, pf, edge_off, node_off, V, multiplier=1.0):
     if rc != 0:
         raise RuntimeError(f"alignn_b200_virial_stress -> {rc}")
     return out
+
+
+def radius_scan_device(lib, X, shifts, cutoff, atol=1e-5):
+    """X [N,3], shifts [I,3]: float64 CUDA tensors -> (u, v, image_index int32, r float32 [E,3]) in (u, c, v) order."""
+    import torch
+    from alignn_b200._lib import stream_ptr
+    _sig(lib)
+    N, I, dev = X.shape[0], shifts.shape[0], X.device
+    off = torch.empty(N + 1, device=dev, dtype=torch.int32)
+    nb = lib.alignn_b200_radius_graph_workspace_bytes(N)
+    ws = torch.empty(max(nb, 1), device=dev, dtype=torch.uint8)
+    rc = lib.alignn_b200_radius_graph_offsets(X.data_ptr(), shifts.data_ptr(), N, I, cutoff, atol, off.data_ptr(), ws.data_ptr(),
+                                              nb, stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"alignn_b200_radius_graph_offsets -> {rc}")
+    E = int(off[-1].item())
+    u, v, c = (torch.empty(E, device=dev, dtype=torch.int32) for _ in range(3))
+    r = torch.empty(E, 3, device=dev, dtype=torch.float32)
+    rc = lib.alignn_b200_radius_graph_fill(X.data_ptr(), shifts.data_ptr(), N, I, cutoff, atol, off.data_ptr(), u.data_ptr(),
+                                           v.data_ptr(), c.data_ptr(), r.data_ptr(), stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"alignn_b200_radius_graph_fill -> {rc}")
+    return u, v, c, r
