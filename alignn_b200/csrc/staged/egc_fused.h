@@ -31,6 +31,8 @@ typedef struct {
   int32_t norm_edges;   /* ALIGNN_NORM_STATS (train BatchNorm: M + column partials), ALIGNN_NORM_AFFINE (eval BatchNorm)
                            or ALIGNN_NORM_LAYER (LayerNorm) */
   int32_t residual;
+  int32_t epilogue_groups; /* 1: four epilogue warps, 32-column chunks; 2: eight warps in two groups that alternate
+                              16-column chunks (row phase of one overlaps the column phase of the other) */
   float gate_eps, ln_eps;
   const float* y;        /* [Ne,d] edge features = A operand of the gate GEMM */
   const void* w_image;   /* alignn_b200_gemm_prepare_weights(W_eg, N=d, K=d) */

@@ -31,36 +31,43 @@ namespace fused {
 constexpr int BM = ALIGNN_FUSED_TILE_ROWS;
 constexpr int BK = 32;
 constexpr int STAGES = 3;
-constexpr int EPI_WARPS = 4;
-constexpr int EPI_THREADS = 32 * EPI_WARPS;
 constexpr int LOAD_WARPS = 8;
-constexpr int THREADS = 32 * (1 + EPI_WARPS + LOAD_WARPS);   // 416
+constexpr int GROUP_THREADS = 128;            // one epilogue group = 4 warps = one thread per tile row
 constexpr uint32_t LBO = 128;
 constexpr uint32_t SBO = (BK / 8) * 128;
-constexpr int CC = 32;            // columns per epilogue chunk
-constexpr int STG = CC + 4;       // staging row stride in floats (16-byte aligned rows, conflict-free both ways)
 constexpr int kSMs = 148;
 
 static std::atomic<int> g_last_cuda_error{0};
 
-template <int D>
+// EG = number of epilogue groups.  With two groups the column chunks alternate between them, so one group's row
+// phase (L2 gathers, MUFU) overlaps the other's column phase; chunks are then 16 columns wide to keep the staging
+// tiles inside the shared-memory budget.
+template <int D, int EG>
 struct Cfg {
+  static constexpr int EPI_WARPS = 4 * EG;
+  static constexpr int THREADS = 32 * (1 + EPI_WARPS + LOAD_WARPS);   // 416 / 544
+  static constexpr int CC = 32 / EG;            // columns per epilogue chunk
+  static constexpr int NG = GROUP_THREADS / CC; // row groups of the column phase (4 / 8)
+  static constexpr int STG = CC + 4;            // staging row stride in floats (16-byte rows, conflict-free both ways)
   static constexpr int A_PLANE = BM * BK * 2;
   static constexpr int B_PLANE = D * BK * 2;
   static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
   static constexpr int PIPE_BYTES = STAGES * STAGE;
-  static constexpr int STG_OFF = PIPE_BYTES;                    // sigma | Bh | m   [3][BM][STG] floats
-  static constexpr int STG_BYTES = 3 * BM * STG * 4;
-  static constexpr int STAT_OFF = STG_OFF + STG_BYTES;          // [EPI_WARPS][2][D] floats
-  static constexpr int STAT_BYTES = EPI_WARPS * 2 * D * 4;
+  static constexpr int STG_OFF = PIPE_BYTES;                    // per group: sigma | Bh | m   [3][BM][STG] floats
+  static constexpr int STG_GROUP = 3 * BM * STG * 4;
+  static constexpr int STAT_OFF = STG_OFF + EG * STG_GROUP;     // [NG][2][D] floats (a column belongs to one group)
+  static constexpr int STAT_BYTES = NG * 2 * D * 4;
   static constexpr int VEC_OFF = STAT_OFF + STAT_BYTES;         // bias | e_w | e_b
   static constexpr int VEC_BYTES = 3 * D * 4;
-  static constexpr int SEG_OFF = VEC_OFF + VEC_BYTES;           // [BM + 1] tile-local segment starts
-  static constexpr int SEG_BYTES = ((BM + 1) * 4 + 15) / 16 * 16;
-  static constexpr int BAR_OFF = SEG_OFF + SEG_BYTES;
+  static constexpr int SEG_OFF = VEC_OFF + VEC_BYTES;           // per group: [BM + 1] tile-local segment starts
+  static constexpr int SEG_GROUP = ((BM + 1) * 4 + 15) / 16 * 16;
+  static constexpr int XCH_OFF = SEG_OFF + EG * SEG_GROUP;      // [EG][BM] floats: LayerNorm row statistics exchange
+  static constexpr int XCH_BYTES = EG * BM * 4;
+  static constexpr int BAR_OFF = XCH_OFF + XCH_BYTES;
   static constexpr int SMEM = BAR_OFF + 128;
   static constexpr int TMEM_COLS = 2 * D < 32 ? 32 : 2 * D;     // double-buffered accumulator
   static_assert(SMEM <= 232448, "shared memory budget of one sm_100 CTA");
+  static_assert(D % (EG * CC) == 0, "chunks must tile the row");
 };
 
 __host__ __device__ constexpr int plane_off(int r, int k) { return (r >> 3) * (int)SBO + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2; }
@@ -73,38 +80,76 @@ __device__ __forceinline__ void a_coord(int i, int lt, int& row, int& kq) {
   kq = (u & 1) * 4 + (lane >> 4) * 2 + (lane & 1);
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+// named barriers: 1 + group for one epilogue group, 3 for all epilogue warps
+__device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GROUP_THREADS) : "memory"); }
+template <int EG>
+__device__ __forceinline__ void all_epi_bar() { asm volatile("bar.sync 3, %0;" ::"n"(EG * GROUP_THREADS) : "memory"); }
 
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
-        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
-        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
-        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
-        "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])),
-        "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])),
-        "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])),
-        "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])),
-        "r"(__float_as_uint(v[31]))
-      : "memory");
+// TMEM <-> registers, 32 lanes x N columns of fp32 (thread t of the warp <-> lane base + t)
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]) {
+  static_assert(N == 16 || N == 32, "chunk width");
+  uint32_t r[N];
+  if constexpr (N == 32) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+  }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int N>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const float (&v)[N]) {
+  static_assert(N == 16 || N == 32, "chunk width");
+#define U(i) "r"(__float_as_uint(v[i]))
+  if constexpr (N == 32) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), U(0), U(1), U(2), U(3), U(4), U(5), U(6), U(7), U(8), U(9), U(10), U(11), U(12), U(13), U(14), U(15),
+          U(16), U(17), U(18), U(19), U(20), U(21), U(22), U(23), U(24), U(25), U(26), U(27), U(28), U(29), U(30), U(31)
+        : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), U(0), U(1), U(2), U(3), U(4), U(5), U(6), U(7), U(8), U(9), U(10), U(11), U(12), U(13), U(14), U(15)
+        : "memory");
+  }
+#undef U
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }   // as common.cuh
 __device__ __forceinline__ float silu_(float u) { return u * sigmoidf_(u); }
 
-template <int D>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int D, int EG>
+__global__ void __launch_bounds__(Cfg<D, EG>::THREADS, 1)
 egc_forward_fused_kernel(const alignn_b200_egc_fused_fwd_args a) {
-  using F = Cfg<D>;
+  using F = Cfg<D, EG>;
+  constexpr int CC = F::CC, STG = F::STG, NG = F::NG, EPI_WARPS = F::EPI_WARPS;
   extern __shared__ __align__(128) uint8_t smem[];
-  float* stg = reinterpret_cast<float*>(smem + F::STG_OFF);
   float* stat = reinterpret_cast<float*>(smem + F::STAT_OFF);
   float* vec = reinterpret_cast<float*>(smem + F::VEC_OFF);
-  int* seg = reinterpret_cast<int*>(smem + F::SEG_OFF);
+  float* xch = reinterpret_cast<float*>(smem + F::XCH_OFF);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + F::BAR_OFF);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
@@ -214,22 +259,28 @@ egc_forward_fused_kernel(const alignn_b200_egc_fused_fwd_args a) {
   } else if (warp >= 1) {
     // ================= epilogue =================
     const int q = warp & 3;                   // TMEM lane quarter this warp may access = its 32 tile rows
+    const int grp = (warp - 1) >> 2;          // epilogue group: owns chunks grp, grp + EG, ...
     const int et = q * 32 + lane;             // tile row owned in the row phase (and: which seg[] entry it fills)
-    float* sig = stg;
-    float* sgc = stg + BM * STG;
-    float* mst = stg + 2 * BM * STG;
+    const int ea = grp * GROUP_THREADS + et;  // index among all epilogue threads
+    const int col = et % CC;                  // column phase: this thread's column inside the chunk ...
+    const int rg = et / CC;                   // ... and its row group (segments rg, rg + NG, ...; stat rows of group rg)
+    float* sig = reinterpret_cast<float*>(smem + F::STG_OFF + grp * F::STG_GROUP);
+    float* sgc = sig + BM * STG;
+    float* mst = sig + 2 * BM * STG;
+    int* seg = reinterpret_cast<int*>(smem + F::SEG_OFF + grp * F::SEG_GROUP);
     float* bias_s = vec;
     float* ew_s = vec + D;
     float* eb_s = vec + 2 * D;
     const bool stats = a.norm_edges == ALIGNN_NORM_STATS && a.partials != nullptr;
     const bool affine_out = a.norm_edges == ALIGNN_NORM_AFFINE && a.y_out != nullptr;
     const bool layer_out = a.norm_edges == ALIGNN_NORM_LAYER && a.y_out != nullptr;
-    for (int i = et; i < D; i += EPI_THREADS) {
+    for (int i = ea; i < D; i += EG * GROUP_THREADS) {
       bias_s[i] = a.bias ? a.bias[i] : 0.f;
       ew_s[i] = a.e_w ? a.e_w[i] : 0.f;
       eb_s[i] = a.e_b ? a.e_b[i] : 0.f;
     }
-    for (int i = et; i < EPI_WARPS * 2 * D; i += EPI_THREADS) stat[i] = 0.f;
+    for (int i = ea; i < NG * 2 * D; i += EG * GROUP_THREADS) stat[i] = 0.f;
+    all_epi_bar<EG>();                        // vec / stat initialised for every group
 
     // per-tile row metadata, fetched one tile ahead (descriptor -> in_eid -> src/dst is a dependent chain)
     int4 n_desc = make_int4(0, 0, 0, 0);
@@ -254,7 +305,7 @@ egc_forward_fused_kernel(const alignn_b200_egc_fused_fwd_args a) {
       const int v0 = desc.x, nseg = desc.y, rows = desc.w;
       const bool valid = et < rows;
       const int64_t e = n_e, s = n_s, t = n_t;
-      epi_bar();                              // previous tile's column phase is done with seg[] (and vec/stat are set)
+      // (the group's last barrier of the previous tile already fenced its reads of seg[])
       if (et <= nseg) seg[et] = n_seg;
       if (et == 0 && nseg == BM) seg[BM] = n_seg_last;
       fetch_meta(tile + gridDim.x);
@@ -265,10 +316,10 @@ egc_forward_fused_kernel(const alignn_b200_egc_fused_fwd_args a) {
       const float* pb = a.P + t * 4 * D + 2 * D;      // e_dst of the destination row
       float row_sum = 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < D; c0 += CC) {
+      for (int c0 = grp * CC; c0 < D; c0 += EG * CC) {
         // ---------------- row phase ----------------
         float v[CC];
-        tc::tmem_ld32(trow + (uint32_t)c0, v);
+        tmem_ld<CC>(trow + (uint32_t)c0, v);
         float* srow = sig + et * STG;
         float* crow = sgc + et * STG;
         float* mrow = mst + et * STG;
@@ -326,56 +377,76 @@ egc_forward_fused_kernel(const alignn_b200_egc_fused_fwd_args a) {
         }
         // LayerNorm: keep m in the accumulator for the two passes below.  tcgen05.st is warp-collective
         // (.sync.aligned), so it sits outside the `valid` branch; rows past the tile's end store junk nobody reads.
-        if (layer_out) tmem_st32(trow + (uint32_t)c0, v);
-        epi_bar();
-        // ---------------- column phase: thread = (column `lane`, segment group q) ----------------
-        for (int j = q; j < nseg; j += EPI_WARPS) {
+        if (layer_out) tmem_st<CC>(trow + (uint32_t)c0, v);
+        group_bar(grp);
+        // ---------------- column phase: thread = (column `col`, row group `rg`) ----------------
+        for (int j = rg; j < nseg; j += NG) {
           const int64_t vtx = v0 + j;
-          const float dv = __ldg(a.P + vtx * 4 * D + 3 * D + c0 + lane);
+          const float dv = __ldg(a.P + vtx * 4 * D + 3 * D + c0 + col);
           const int r0 = seg[j], r1 = seg[j + 1];
           float s1 = 0.f, s2 = 0.f;
           for (int r = r0; r < r1; ++r) {
-            const float g = sig[r * STG + lane];
+            const float g = sig[r * STG + col];
             s1 += g;
-            s2 = fmaf(sgc[r * STG + lane], g, s2);   // Bh * sigma, fused and in edge order like the row-per-warp kernel
+            s2 = fmaf(sgc[r * STG + col], g, s2);   // Bh * sigma, fused and in edge order like the row-per-warp kernel
           }
           const float h = s2 / (s1 + a.gate_eps);
-          a.XP[vtx * D + c0 + lane] = dv + h;
+          a.XP[vtx * D + c0 + col] = dv + h;
           if (a.S) {
-            a.S[vtx * D + c0 + lane] = s1;
-            a.H[vtx * D + c0 + lane] = h;
+            a.S[vtx * D + c0 + col] = s1;
+            a.H[vtx * D + c0 + col] = h;
           }
         }
         if (stats) {
           float t1 = 0.f, t2 = 0.f;
 #pragma unroll 8
-          for (int r = q * 32; r < q * 32 + 32; ++r) {
-            const float x = mst[r * STG + lane];
+          for (int r = rg * (BM / NG); r < (rg + 1) * (BM / NG); ++r) {
+            const float x = mst[r * STG + col];
             t1 += x;
             t2 += x * x;
           }
-          stat[(q * 2 + 0) * D + c0 + lane] += t1;
-          stat[(q * 2 + 1) * D + c0 + lane] += t2;
+          stat[(rg * 2 + 0) * D + c0 + col] += t1;
+          stat[(rg * 2 + 1) * D + c0 + col] += t2;
         }
-        epi_bar();                             // staging tile free for the next chunk
+        group_bar(grp);                        // staging tile (and, after the last chunk, seg[]) free again
       }
       if (layer_out) {
         // two more passes over the row in TMEM: variance about the mean (two-pass, like torch), then the output.
-        // Every lane runs the warp-collective tcgen05.ld; only rows inside the tile store.
-        const float mean = row_sum * (1.f / D);
+        // Every lane runs the warp-collective tcgen05.ld; only rows inside the tile store.  With two groups each
+        // holds the statistics of its own chunks: exchange through shared memory.
+        float mean;
+        if constexpr (EG == 1) {
+          mean = row_sum * (1.f / D);
+        } else {
+          xch[grp * BM + et] = row_sum;
+          all_epi_bar<EG>();
+          float tot = 0.f;
+#pragma unroll
+          for (int g2 = 0; g2 < EG; ++g2) tot += xch[g2 * BM + et];
+          mean = tot * (1.f / D);
+          all_epi_bar<EG>();
+        }
         float qsum = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < D; c0 += CC) {
+        for (int c0 = grp * CC; c0 < D; c0 += EG * CC) {
           float v[CC];
-          tc::tmem_ld32(trow + (uint32_t)c0, v);
+          tmem_ld<CC>(trow + (uint32_t)c0, v);
 #pragma unroll
           for (int j = 0; j < CC; ++j) { const float dlt = v[j] - mean; qsum += dlt * dlt; }
         }
+        if constexpr (EG > 1) {
+          xch[grp * BM + et] = qsum;
+          all_epi_bar<EG>();
+          qsum = 0.f;
+#pragma unroll
+          for (int g2 = 0; g2 < EG; ++g2) qsum += xch[g2 * BM + et];
+          all_epi_bar<EG>();
+        }
         const float rstd = rsqrtf(qsum * (1.f / D) + a.ln_eps);
 #pragma unroll 1
-        for (int c0 = 0; c0 < D; c0 += CC) {
+        for (int c0 = grp * CC; c0 < D; c0 += EG * CC) {
           float v[CC];
-          tc::tmem_ld32(trow + (uint32_t)c0, v);
+          tmem_ld<CC>(trow + (uint32_t)c0, v);
           if (valid) {
             float4* yo = reinterpret_cast<float4*>(a.y_out + e * D + c0);
             const float4* yi = reinterpret_cast<const float4*>(a.y + e * D + c0);
@@ -398,14 +469,14 @@ egc_forward_fused_kernel(const alignn_b200_egc_fused_fwd_args a) {
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty[acc]);
     }
-    if (stats) {                               // fixed-order sum over the four row groups -> one partial row per CTA
-      epi_bar();
+    if (stats) {                               // fixed-order sum over the row groups -> one partial row per CTA
+      all_epi_bar<EG>();
       float* out_row = a.partials + (int64_t)blockIdx.x * 2 * D;
-      for (int i = et; i < 2 * D; i += EPI_THREADS) {
+      for (int i = ea; i < 2 * D; i += EG * GROUP_THREADS) {
         const int which = i / D, c = i % D;
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < EPI_WARPS; ++w) t += stat[(w * 2 + which) * D + c];
+        for (int w = 0; w < NG; ++w) t += stat[(w * 2 + which) * D + c];
         out_row[i] = t;
       }
     }
@@ -447,17 +518,17 @@ egc_forward_fused_kernel(const alignn_b200_egc_fused_fwd_args a) {
   if (warp == 0) tc::tmem_dealloc(tmem, F::TMEM_COLS);
 }
 
-template <int D>
+template <int D, int EG>
 int launch(const alignn_b200_egc_fused_fwd_args& a) {
-  using F = Cfg<D>;
+  using F = Cfg<D, EG>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(egc_forward_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(egc_forward_fused_kernel<D, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
     if (e != cudaSuccess) { g_last_cuda_error.store((int)e); return ALIGNN_ERR_CUDA; }
     configured = true;
   }
   const int grid = a.num_tiles < kSMs ? a.num_tiles : kSMs;
-  egc_forward_fused_kernel<D><<<grid, THREADS, F::SMEM, (cudaStream_t)a.stream>>>(a);
+  egc_forward_fused_kernel<D, EG><<<grid, F::THREADS, F::SMEM, (cudaStream_t)a.stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_cuda_error.store((int)e); return ALIGNN_ERR_CUDA; }
   return ALIGNN_OK;
@@ -514,12 +585,15 @@ int alignn_b200_egc_forward_fused(const alignn_b200_egc_fused_fwd_args* a) {
   if (a->norm_edges == ALIGNN_NORM_STATS && (!a->partials || (a->Ne > 0 && !a->M))) return ALIGNN_ERR_BAD_ARG;
   if (a->y_out && (!a->e_w || !a->e_b)) return ALIGNN_ERR_BAD_ARG;
   if (((uintptr_t)a->tiles & 15) != 0) return ALIGNN_ERR_BAD_ARG;   // descriptors are read as int4
+  if (a->epilogue_groups != 1 && a->epilogue_groups != 2) return ALIGNN_ERR_BAD_ARG;
+#define ALIGNN_FUSED_LAUNCH(DD) (a->epilogue_groups == 2 ? alignn::fused::launch<DD, 2>(*a) : alignn::fused::launch<DD, 1>(*a))
   switch (a->d) {
-    case 256: return alignn::fused::launch<256>(*a);
-    case 128: return alignn::fused::launch<128>(*a);
-    case 64: return alignn::fused::launch<64>(*a);
-    default: return alignn::fused::launch<32>(*a);
+    case 256: return ALIGNN_FUSED_LAUNCH(256);
+    case 128: return ALIGNN_FUSED_LAUNCH(128);
+    case 64: return ALIGNN_FUSED_LAUNCH(64);
+    default: return ALIGNN_FUSED_LAUNCH(32);
   }
+#undef ALIGNN_FUSED_LAUNCH
 }
 
 }  // extern "C"

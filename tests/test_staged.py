@@ -51,6 +51,17 @@ def test_tile_packer_covers_every_segment_once(staged, degs):
     assert v == len(degs)
 
 
+def test_ctypes_struct_matches_staged_header(staged):
+    """The library rejects a binding whose struct layout drifted (struct_size guard); Nn = 0 returns before any CUDA call."""
+    import ctypes as C
+    import staged_binding
+    a = staged_binding.FusedArgs(struct_size=C.sizeof(staged_binding.FusedArgs), Nn=0, Ne=0, d=64, norm_edges=2, residual=1,
+                                 epilogue_groups=1)
+    assert staged.alignn_b200_egc_forward_fused(C.byref(a)) == 0
+    a.struct_size += 8
+    assert staged.alignn_b200_egc_forward_fused(C.byref(a)) != 0
+
+
 def test_tile_packer_rejects_oversized_segment(staged):
     in_ptr = np.array([0, 5, 134, 140], dtype=np.int32)
     assert pack_tiles(staged, in_ptr)[0] == -2
@@ -127,7 +138,7 @@ needs_optin = pytest.mark.skipif(os.environ.get("ALIGNN_B200_STAGED") != "1",
                                  reason="staged kernel: opt in with ALIGNN_B200_STAGED=1 (not yet validated on hardware)")
 
 
-def _run_fused(lib, gr, x, y, conv_w, norm_edges, d, train, e_w=None, e_b=None, residual=True):
+def _run_fused(lib, gr, x, y, conv_w, norm_edges, d, train, e_w=None, e_b=None, residual=True, groups=1):
     """Returns the fused kernel's outputs and the shipped two-kernel path's, on the same inputs."""
     import staged_binding
     from alignn_b200 import ops
@@ -139,7 +150,8 @@ def _run_fused(lib, gr, x, y, conv_w, norm_edges, d, train, e_w=None, e_b=None, 
     n, tiles = pack_tiles(lib, ix.in_ptr.cpu().numpy())
     assert n > 0
     tiles_d = torch.from_numpy(tiles).to(dev)
-    out = staged_binding.fused_forward(lib, ix, tiles_d, n, y, img, b_eg, P, norm_edges, train, e_w, e_b, residual)
+    out = staged_binding.fused_forward(lib, ix, tiles_d, n, y, img, b_eg, P, norm_edges, train, e_w, e_b, residual,
+                                       groups=groups)
     torch.cuda.synchronize()
     G = ops.gemm_nt(y, img, b_eg)
     zeros = torch.zeros(d, device=dev)
@@ -152,9 +164,10 @@ def _run_fused(lib, gr, x, y, conv_w, norm_edges, d, train, e_w=None, e_b=None, 
 
 @pytest.mark.gpu
 @needs_optin
+@pytest.mark.parametrize("groups", [1, 2])
 @pytest.mark.parametrize("d", [256, 64])
 @pytest.mark.parametrize("shuffle", [False, True])
-def test_fused_forward_bit_identical_to_shipped_path(staged, d, shuffle):
+def test_fused_forward_bit_identical_to_shipped_path(staged, d, shuffle, groups):
     from alignn_b200 import ops
     dev = torch.device("cuda:0")
     g, lg, _, _ = synthetic.make_batch(batch_size=4, atoms=9, k=12, seed=17, vary_atoms=True)
@@ -171,17 +184,17 @@ def test_fused_forward_bit_identical_to_shipped_path(staged, d, shuffle):
         bcat, b_eg = torch.randn(4 * d, generator=gen).to(dev), torch.randn(d, generator=gen).to(dev)
         e_w, e_b = (torch.rand(d, generator=gen) + 0.5).to(dev), torch.randn(d, generator=gen).to(dev)
         # training BatchNorm: M, S, H, x' bit-identical; column sums to fp32 round-off
-        out, ref = _run_fused(staged, grd, x, y, (Wcat, bcat, W_eg, b_eg), ops.NORM_STATS, d, True)
+        out, ref = _run_fused(staged, grd, x, y, (Wcat, bcat, W_eg, b_eg), ops.NORM_STATS, d, True, groups=groups)
         for k in ("M", "S", "H", "XP"):
             assert torch.equal(out[k], ref[k]), k
         sums = out["partials"].double().sum(0)
         refs = ref["partials"].double().sum(0)[:2]
         assert torch.allclose(sums, refs, rtol=1e-5, atol=1e-3)
         # eval BatchNorm: y_out bit-identical; LayerNorm: the row statistics are summed in a different order
-        out, ref = _run_fused(staged, grd, x, y, (Wcat, bcat, W_eg, b_eg), ops.NORM_AFFINE, d, False, e_w, e_b)
+        out, ref = _run_fused(staged, grd, x, y, (Wcat, bcat, W_eg, b_eg), ops.NORM_AFFINE, d, False, e_w, e_b, groups=groups)
         assert torch.equal(out["y_out"], ref["y_out"])
         assert torch.equal(out["XP"], ref["XP"])
-        out, ref = _run_fused(staged, grd, x, y, (Wcat, bcat, W_eg, b_eg), ops.NORM_LAYER, d, True, e_w, e_b)
+        out, ref = _run_fused(staged, grd, x, y, (Wcat, bcat, W_eg, b_eg), ops.NORM_LAYER, d, True, e_w, e_b, groups=groups)
         assert torch.equal(out["M"], ref["M"])
         err = (out["y_out"] - ref["y_out"]).abs().max().item()
         assert err <= 1e-5 * max(ref["y_out"].abs().max().item(), 1.0), err
@@ -189,8 +202,9 @@ def test_fused_forward_bit_identical_to_shipped_path(staged, d, shuffle):
 
 @pytest.mark.gpu
 @needs_optin
+@pytest.mark.parametrize("groups", [1, 2])
 @pytest.mark.parametrize("mode", ["layernorm", "bn_eval", "bn_train"])
-def test_fused_conv_forward_matches_shipped_forward(staged, mode):
+def test_fused_conv_forward_matches_shipped_forward(staged, mode, groups):
     """Fused kernel + node tail against `ops.egc_forward` (+ the BatchNorm finalize/apply steps) end to end."""
     import staged_binding
     from alignn_b200 import ops
@@ -215,7 +229,7 @@ def test_fused_conv_forward_matches_shipped_forward(staged, mode):
         norm = {"layernorm": ops.NORM_LAYER, "bn_eval": ops.NORM_AFFINE, "bn_train": ops.NORM_STATS}[mode]
         kw = dict(norm_nodes=norm, norm_edges=norm, residual=True, save=True, need_edge_out=True)
         ref = ops.egc_forward(ix, x, y, G, P, n_w, n_b, e_w, e_b, **kw)
-        out = staged_binding.conv_forward_like(staged, ix, tiles_d, n, x, y, img, b_eg, P, n_w, n_b, e_w, e_b, **kw)
+        out = staged_binding.conv_forward_like(staged, ix, tiles_d, n, x, y, img, b_eg, P, n_w, n_b, e_w, e_b, groups=groups, **kw)
         torch.cuda.synchronize()
         for k in ("M", "XP", "S", "H"):
             assert torch.equal(out[k], ref[k]), (mode, k)

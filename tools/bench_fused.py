@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--d", type=int, default=256)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--mode", choices=["stats", "affine", "layer"], default="stats")
+    ap.add_argument("--groups", type=int, choices=[1, 2], default=1, help="epilogue groups of the fused kernel")
     args = ap.parse_args()
     import staged_binding as SB
     from alignn_b200 import ops, synthetic
@@ -52,7 +53,7 @@ def main():
         ones, zeros = torch.ones(d, device=dev), torch.zeros(d, device=dev)
 
         def fused(out=None):
-            return SB.fused_forward(lib, ix, tiles_d, n, y, img, b_eg, P, norm, train, e_w, e_b, out=out)
+            return SB.fused_forward(lib, ix, tiles_d, n, y, img, b_eg, P, norm, train, e_w, e_b, out=out, groups=args.groups)
 
         def shipped():
             G = ops.gemm_nt(y, img, b_eg)
@@ -80,7 +81,7 @@ def main():
         nbytes = 4 * d * (Ne * (1 + int(train) + (args.mode != "stats") * 2) + Nn * (4 + 1 + 2 * int(train))) + 12 * Ne
         res[name] = dict(Nn=Nn, Ne=Ne, tiles=n, fused_us=round(t_f, 1), shipped_us=round(t_s, 1),
                          fused_algorithmic_GBps=round(nbytes / t_f / 1e3, 1))
-    print(json.dumps(dict(bench="fused_gate_forward", mode=args.mode, d=d, batch=args.batch, **res)))
+    print(json.dumps(dict(bench="fused_gate_forward", mode=args.mode, groups=args.groups, d=d, batch=args.batch, **res)))
 
 
 if __name__ == "__main__":

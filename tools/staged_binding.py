@@ -10,7 +10,8 @@ import build_staged
 
 class FusedArgs(C.Structure):
     _fields_ = [("struct_size", C.c_size_t), ("Nn", C.c_int64), ("Ne", C.c_int64), ("d", C.c_int32),
-                ("norm_edges", C.c_int32), ("residual", C.c_int32), ("gate_eps", C.c_float), ("ln_eps", C.c_float),
+                ("norm_edges", C.c_int32), ("residual", C.c_int32), ("epilogue_groups", C.c_int32),
+                ("gate_eps", C.c_float), ("ln_eps", C.c_float),
                 ("y", C.c_void_p), ("w_image", C.c_void_p), ("bias", C.c_void_p), ("P", C.c_void_p),
                 ("src", C.c_void_p), ("dst", C.c_void_p), ("in_ptr", C.c_void_p), ("in_eid", C.c_void_p),
                 ("tiles", C.c_void_p), ("num_tiles", C.c_int32), ("e_w", C.c_void_p), ("e_b", C.c_void_p),
@@ -50,7 +51,7 @@ def pack_tiles(lib, in_ptr: np.ndarray):
 
 
 def fused_forward(lib, ix, tiles_d, n_tiles, y, img, b_eg, P, norm_edges, train, e_w=None, e_b=None, residual=True,
-                  out=None, need_edge_out=True):
+                  out=None, need_edge_out=True, groups=1):
     """Launch the fused kernel on torch's current stream.  `out` (a dict from a previous call) is reused if given."""
     import torch
     from alignn_b200 import ops
@@ -65,7 +66,7 @@ def fused_forward(lib, ix, tiles_d, n_tiles, y, img, b_eg, P, norm_edges, train,
                    H=new(Nn, d) if train else None, partials=new(rows, 2, d) if norm_edges == ops.NORM_STATS else None,
                    y_out=new(Ne, d) if (norm_edges != ops.NORM_STATS and need_edge_out) else None)
     a = FusedArgs(struct_size=C.sizeof(FusedArgs), Nn=Nn, Ne=Ne, d=d, norm_edges=norm_edges, residual=int(residual),
-                  gate_eps=1e-6, ln_eps=1e-5, y=ptr(y), w_image=ops.ptr_any(img.buf), bias=ptr(b_eg), P=ptr(P),
+                  epilogue_groups=groups, gate_eps=1e-6, ln_eps=1e-5, y=ptr(y), w_image=ops.ptr_any(img.buf), bias=ptr(b_eg), P=ptr(P),
                   src=ptr(ix.src), dst=ptr(ix.dst), in_ptr=ptr(ix.in_ptr), in_eid=None if ix.dst_sorted else ptr(ix.in_eid),
                   tiles=ptr(tiles_d), num_tiles=n_tiles, e_w=ptr(e_w), e_b=ptr(e_b), M=ptr(out["M"]), y_out=ptr(out["y_out"]),
                   XP=ptr(out["XP"]), S=ptr(out["S"]), H=ptr(out["H"]), partials=ptr(out["partials"]), stream=stream_ptr())
@@ -76,7 +77,7 @@ def fused_forward(lib, ix, tiles_d, n_tiles, y, img, b_eg, P, norm_edges, train,
 
 
 def conv_forward_like(lib, ix, tiles_d, n_tiles, x, y, img, b_eg, P, n_w, n_b, e_w, e_b, *, norm_nodes, norm_edges,
-                      residual=True, save=True, need_edge_out=True):
+                      residual=True, save=True, need_edge_out=True, groups=1):
     """The whole post-Linear forward of one conv built from the fused kernel + node tail, with the output contract of
     `alignn_b200.ops.egc_forward` (x_out / y_out are None in STATS mode; partials_e / partials_n then feed
     `ops.bn_finalize(..., which=0, ...)`).  This is what conv.py will call once the kernel is validated."""
@@ -88,7 +89,7 @@ def conv_forward_like(lib, ix, tiles_d, n_tiles, x, y, img, b_eg, P, n_w, n_b, e
     stats = norm_nodes == ops.NORM_STATS or norm_edges == ops.NORM_STATS
     train = save or stats
     out = fused_forward(lib, ix, tiles_d, n_tiles, y, img, b_eg, P, norm_edges, train, e_w, e_b, residual,
-                        need_edge_out=need_edge_out)
+                        need_edge_out=need_edge_out, groups=groups)
     out["partials_e"] = out.pop("partials")
     out["partials_n"] = None
     out["x_out"] = None

@@ -18,7 +18,9 @@ echo "fused forward: exit $rc"; tail -15 gpurun_out/staged_fused_tests.log
 # 3. timing only if it is correct
 if [ $rc -eq 0 ]; then
   for mode in stats affine layer; do
-    timeout 300 python tools/bench_fused.py --mode $mode >> gpurun_out/staged_bench_fused.jsonl 2>> gpurun_out/staged_bench_fused.err
+    for groups in 1 2; do
+      timeout 300 python tools/bench_fused.py --mode $mode --groups $groups >> gpurun_out/staged_bench_fused.jsonl 2>> gpurun_out/staged_bench_fused.err
+    done
   done
   cat gpurun_out/staged_bench_fused.jsonl
 fi
