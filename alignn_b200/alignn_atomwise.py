@@ -92,6 +92,16 @@ class ALIGNNAtomWiseConfig(BaseSettings):
     additional_output_weight: float = 0
 
 
+def cutoff_function_based_edges(r: torch.Tensor, inner_cutoff: float = 4, exponent: int = 3) -> torch.Tensor:
+    """Polynomial envelope 1 + c1 x^p + c2 x^(p+1) + c3 x^(p+2), x = r / inner_cutoff, zero beyond the cutoff
+    (alignn/models/utils.py:58-86)."""
+    p = exponent
+    x = r / inner_cutoff
+    c1, c2, c3 = -(p + 1) * (p + 2) / 2, p * (p + 2), -p * (p + 1) / 2
+    env = 1 + c1 * x ** p + c2 * x ** (p + 1) + c3 * x ** (p + 2)
+    return torch.where(r <= inner_cutoff, env, torch.zeros_like(r))
+
+
 EV_PER_A3_IN_GPA = 160.21766208          # 1 eV/A^3 in GPa (alignn_atomwise.py:569)
 
 
@@ -119,13 +129,14 @@ class ALIGNNAtomWise(nn.Module):
     Forces use first-order autograd only (`create_graph=False`): the conv's autograd Function is
     once-differentiable, so FF *training* on forces (double backward, :536) is not available.
     Stress: the batched virial of :610-638 (`batch_stress=True`, the default) from the same pair forces.
-    Not built: `batch_stress=False` (:573-590), include_pos_deriv, cutoff-function variants.
+    Cutoff envelope on the bond lengths (`use_cutoff_function`, both `multiply_cutoff` settings, :434-451).
+    Not built: `batch_stress=False` (:573-590), include_pos_deriv.
     """
 
     def __init__(self, config: ALIGNNAtomWiseConfig = ALIGNNAtomWiseConfig(name="alignn_atomwise")):
         super().__init__()
         c = self.config = config
-        for flag, why in ((c.include_pos_deriv, "include_pos_deriv"), (c.use_cutoff_function, "use_cutoff_function"),
+        for flag, why in ((c.include_pos_deriv, "include_pos_deriv"),
                           (c.stresswise_weight != 0 and not c.batch_stress, "stresswise_weight != 0 with batch_stress=False"),
                           (c.stresswise_weight != 0 and not c.calculate_gradient, "stress without calculate_gradient"),
                           (c.extra_features != 0, "extra_features")):
@@ -175,7 +186,15 @@ class ALIGNNAtomWise(nn.Module):
             # lg_on_fly (:424-431): cosines recomputed from r so that the three-body terms are in the autograd graph
             h = bond_cosines(r, lg) if (c.lg_on_fly or c.calculate_gradient) else lg.edata["h"]
             z = self.angle_embedding(h)
-        y = self.edge_embedding(bondlength)
+        if c.use_cutoff_function:                                   # (:434-451)
+            env = cutoff_function_based_edges(bondlength, inner_cutoff=c.inner_cutoff, exponent=c.exponent)
+            if c.multiply_cutoff:
+                y = self.edge_embedding(bondlength) * env.unsqueeze(1)
+            else:
+                bondlength = env        # the reference rebinds `bondlength`: the penalty below then sees the envelope
+                y = self.edge_embedding(bondlength)
+        else:
+            y = self.edge_embedding(bondlength)
         n_al, n_gcn = len(self.alignn_layers), len(self.gcn_layers)
         for i, layer in enumerate(self.alignn_layers):
             x, y, z = layer(g, lg, x, y, z, _need_z_out=(i + 1 < n_al))
@@ -192,11 +211,15 @@ class ALIGNNAtomWise(nn.Module):
         forces = torch.empty(1)
         stress = torch.empty(1)
         natoms = g.batch_num_nodes().to(out.device).to(out.dtype)
-        en_out = out * natoms if c.energy_mult_natoms else out + 0.0   # (:495-497; no aliasing of `out`, cf. App. D-12)
+        en_out = out * natoms if c.energy_mult_natoms else out          # (:495-497)
         if c.use_penalty:                                               # (:498-510) zero for bonds >= threshold
             pen = torch.where(bondlength < c.penalty_threshold, c.penalty_factor * (c.penalty_threshold - bondlength),
                               torch.zeros_like(bondlength))
             en_out = en_out + pen.sum()
+            if not c.energy_mult_natoms:
+                # the reference does `en_out = out; en_out += total_penalty` in place, so the (whole-batch) penalty also
+                # lands in result["out"]; reproduced, not fixed
+                out = en_out
         if c.calculate_gradient:
             (dr,) = torch.autograd.grad(en_out, r, grad_outputs=torch.ones_like(en_out),
                                         create_graph=False, retain_graph=self.training)

@@ -267,22 +267,51 @@ class ALIGNN(nn.Module):
         return torch.squeeze(out)                                          # :349
 
 
-def energy_and_forces(model: ALIGNN, g: OGraph, lg: OGraph, energy_mult_natoms=True):
-    """Energy + per-atom forces the ALIGNN-FF way (alignn_atomwise.py:404-431,456-467,495-497,526-563).
+def cutoff_envelope(r, inner_cutoff=4, exponent=3):
+    """alignn/models/utils.py:58-86: polynomial envelope of x = r / inner_cutoff, zero beyond the cutoff."""
+    ratio = r / inner_cutoff
+    c1 = -(exponent + 1) * (exponent + 2) / 2
+    c2 = exponent * (exponent + 2)
+    c3 = -exponent * (exponent + 1) / 2
+    env = 1 + c1 * ratio ** exponent + c2 * ratio ** (exponent + 1) + c3 * ratio ** (exponent + 2)
+    return torch.where(r <= inner_cutoff, env, torch.zeros_like(r))
+
+
+def energy_and_forces(model: ALIGNN, g: OGraph, lg: OGraph, energy_mult_natoms=True, use_penalty=True,
+                      penalty_factor=0.1, penalty_threshold=1.0, use_cutoff_function=False, multiply_cutoff=False,
+                      inner_cutoff=3.0, exponent=5):
+    """Energy + per-atom forces the ALIGNN-FF way (alignn_atomwise.py:404-467,495-510,526-563).
 
     r requires grad; cosines recomputed from r inside the autograd graph (lg_on_fly);
-    en = fc(avgpool(x)) * natoms; pair_forces = -dE/dr (grad_multiplier=-1);
-    forces = sum_in-edges pair_forces - sum_out-edges pair_forces.
-    No short-bond penalty (zero for |r| >= 1 A).
+    optional cutoff envelope on the bond lengths (:434-451; without `multiply_cutoff` the envelope REPLACES the bond
+    length, also for the penalty below);
+    en = fc(avgpool(x)) [* natoms] + sum of short-bond penalties (:495-510; with energy_mult_natoms=False the reference
+    adds the penalty in place to `out` itself, so it also appears in result["out"], SURVEY App. D-12);
+    pair_forces = -dE/dr (grad_multiplier=-1); forces = sum_in-edges pair_forces - sum_out-edges pair_forces.
     """
     r = g.edata["r"].detach().clone().requires_grad_(True)
     h = bond_cosines(r, lg.src, lg.dst)
     z = model.angle_embedding(h)
     x = model.atom_embedding(g.ndata["atom_features"])
-    y = model.edge_embedding(torch.norm(r, dim=1))
+    bondlength = torch.norm(r, dim=1)
+    if use_cutoff_function:
+        env = cutoff_envelope(bondlength, inner_cutoff, exponent)
+        if multiply_cutoff:
+            y = model.edge_embedding(bondlength) * env.unsqueeze(1)
+        else:
+            bondlength = env
+            y = model.edge_embedding(bondlength)
+    else:
+        y = model.edge_embedding(bondlength)
     x, y = model.conv_stack(g, lg, x, y, z)
     out = torch.squeeze(model.fc(avg_pool(g, x)))
     en = out * g.bnn.to(out.dtype) if energy_mult_natoms else out
+    if use_penalty:
+        pen = torch.where(bondlength < penalty_threshold, penalty_factor * (penalty_threshold - bondlength),
+                          torch.zeros_like(bondlength))
+        en = en + pen.sum()
+        if not energy_mult_natoms:
+            out = en                                  # the in-place `en_out += total_penalty` on the alias of `out`
     (dr,) = torch.autograd.grad(en.sum(), r)
     pair_forces = -dr
     zeros = torch.zeros(g.n, 3, dtype=r.dtype)

@@ -255,6 +255,28 @@ def main():
                         stresses=res_s["stresses"].detach().numpy(), pair_forces=pair.numpy())
     print("atomwise_stress ok:", tuple(res_s["stresses"].shape))
 
+    # cutoff-envelope variants (alignn_atomwise.py:434-451) and the penalty that leaks into `out` when
+    # energy_mult_natoms=False; shorter bonds so that envelope and penalty are exercised
+    store = {}
+    gg.edata["r"] = gg.edata["r"] * 0.35
+    og_.edata["r"] = og_.edata["r"] * 0.35
+    for tag, extra in (("mult", dict(use_cutoff_function=True, multiply_cutoff=True, inner_cutoff=2.5, exponent=5)),
+                       ("repl", dict(use_cutoff_function=True, multiply_cutoff=False, inner_cutoff=2.5, exponent=3)),
+                       ("leak", dict(use_cutoff_function=False, penalty_threshold=1.2))):
+        cfg_c = {**acfg, "energy_mult_natoms": tag != "leak", **extra}
+        ref_c = ref_atomwise.ALIGNNAtomWise(ref_atomwise.ALIGNNAtomWiseConfig(name="alignn_atomwise", **cfg_c)).to(dtype)
+        GI.fill_state_dict(ref_c, 400)
+        res_c = ref_c((gg, ll, lat.to(dtype)))
+        okw = {k: v for k, v in extra.items()}
+        en_c, f_c, pair_c = O.energy_and_forces(orc, og_, ol_, energy_mult_natoms=tag != "leak", **okw)
+        assert (en_c - res_c["out"].detach()).abs().max() < 1e-10 * max(1.0, float(en_c.abs().max())), tag
+        assert (f_c - res_c["grad"].detach()).abs().max() < 1e-10 * max(1.0, float(f_c.abs().max())), tag
+        store[tag + ".out"] = res_c["out"].detach().numpy()
+        store[tag + ".forces"] = res_c["grad"].detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "atomwise_cutoff.npz"),
+                        in_crc=GI.checksum(*g.edges(), *lg.edges(), g.edata["r"], g.ndata["atom_features"]), **store)
+    print("atomwise_cutoff ok:", {k: float(np.abs(v).max()) for k, v in store.items()})
+
     # ---------------------------------------------------------------- reference test properties (fp64)
     # tests/test_force_reduction.py:212-229 restated on the real reference conv + stub graph ops.
     torch.set_default_dtype(torch.float64)

@@ -300,3 +300,24 @@ def test_atomwise_stress_vs_reference_golden(golden_dir):
     # (2) end to end against the reference.  Each entry is a signed sum over ~100 bonds of r (up to 8 A) x pair force,
     # so the 1e-4 per-bond tolerance of the pair forces (checked above) propagates to ~1e-3 of the largest component.
     assert_close(res["stresses"], gold["stresses"], tol=1e-3, what="stress vs reference")
+
+
+@pytest.mark.parametrize("tag", ["mult", "repl", "leak"])
+def test_atomwise_cutoff_and_penalty_variants_vs_reference_golden(golden_dir, tag):
+    """ALIGNN-FF with the cutoff envelope (both `multiply_cutoff` settings) and with the penalty leaking into `out`
+    (energy_mult_natoms=False) against the unmodified reference; bonds shortened to 0.5-2.8 A as in the fixture."""
+    from alignn_b200.alignn_atomwise import ALIGNNAtomWise, ALIGNNAtomWiseConfig
+    cases = {"mult": dict(use_cutoff_function=True, multiply_cutoff=True, inner_cutoff=2.5, exponent=5),
+             "repl": dict(use_cutoff_function=True, multiply_cutoff=False, inner_cutoff=2.5, exponent=3),
+             "leak": dict(use_cutoff_function=False, penalty_threshold=1.2)}
+    gold = np.load(os.path.join(golden_dir, "atomwise_cutoff.npz"))
+    g, lg, lat, _ = synthetic.make_batch(batch_size=2, atoms=8, k=12, seed=41, vary_atoms=True)
+    g.edata["r"] = g.edata["r"] * 0.35
+    m = ALIGNNAtomWise(ALIGNNAtomWiseConfig(name="alignn_atomwise", alignn_layers=2, gcn_layers=2, hidden_features=64,
+                                            embedding_features=32, atom_input_features=92,
+                                            energy_mult_natoms=tag != "leak", **cases[tag]))
+    GI.fill_state_dict(m, 400)
+    m.to(DEV).eval()
+    res = m((g.to(DEV), lg.to(DEV), lat.to(DEV)))
+    assert_close(res["out"], gold[tag + ".out"], what=f"{tag} energy")
+    assert_close(res["grad"], gold[tag + ".forces"], what=f"{tag} forces")

@@ -120,6 +120,34 @@ def test_atomwise_energy_forces_match_reference(golden_dir):
     np.testing.assert_allclose(pair.numpy(), gold["pair_forces"], rtol=1e-8, atol=1e-10)
 
 
+CUTOFF_CASES = {"mult": dict(use_cutoff_function=True, multiply_cutoff=True, inner_cutoff=2.5, exponent=5),
+                "repl": dict(use_cutoff_function=True, multiply_cutoff=False, inner_cutoff=2.5, exponent=3),
+                "leak": dict(use_cutoff_function=False, penalty_threshold=1.2)}
+
+
+@pytest.mark.parametrize("tag", sorted(CUTOFF_CASES))
+def test_atomwise_cutoff_and_penalty_variants_match_reference(golden_dir, tag):
+    """Cutoff envelope (alignn_atomwise.py:434-451, both `multiply_cutoff` settings) and the short-bond penalty that the
+    reference adds in place to `out` when energy_mult_natoms=False, on bonds shortened to 0.5-2.8 A."""
+    gold = _load(golden_dir, "atomwise_cutoff.npz")
+    g, lg, lat, _ = synthetic.make_batch(batch_size=2, atoms=8, k=12, seed=41, vary_atoms=True)
+    dt = torch.float64
+    m = O.ALIGNN(norm="layernorm", **SMALL_CFG).to(dt)
+    GI.fill_state_dict(m, 400)
+    og = to_oracle(g, dt)
+    og.edata["r"] = og.edata["r"] * 0.35
+    out, forces, _ = O.energy_and_forces(m, og, to_oracle(lg, dt), energy_mult_natoms=tag != "leak", **CUTOFF_CASES[tag])
+    np.testing.assert_allclose(out.numpy(), gold[tag + ".out"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(forces.numpy(), gold[tag + ".forces"], rtol=1e-8, atol=1e-9)
+
+
+def test_cutoff_function_of_the_product_matches_oracle():
+    from alignn_b200.alignn_atomwise import cutoff_function_based_edges
+    r = torch.linspace(0.0, 5.0, 101, dtype=torch.float64)
+    for p, rc in ((3, 4.0), (5, 2.5)):
+        np.testing.assert_allclose(cutoff_function_based_edges(r, rc, p).numpy(), O.cutoff_envelope(r, rc, p).numpy(), rtol=0, atol=0)
+
+
 def test_virial_stress_matches_reference(golden_dir):
     """Batched virial stress (alignn_atomwise.py:610-635) from the reference's own pair forces: the oracle loop and
     the product's segment-sum formulation (a device-agnostic torch tail, no kernel of ours) both reproduce it."""
