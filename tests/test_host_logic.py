@@ -217,3 +217,41 @@ def test_native_structure_builders_edge_cases():
     assert lg.batch_num_edges().tolist() == [2, 0, 6] and lg.num_nodes() == 6
     olg = O.line_graph(to_oracle(bg))
     assert sorted(zip(lg.edges()[0].tolist(), lg.edges()[1].tolist())) == sorted(zip(olg.src.tolist(), olg.dst.tolist()))
+
+
+# ---- property tests on arbitrary small multigraphs (self-loops, parallel edges, isolated nodes, empty) ---------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@st.composite
+def _multigraphs(draw):
+    n = draw(st.integers(min_value=1, max_value=9))
+    e = draw(st.integers(min_value=0, max_value=40))
+    src = draw(st.lists(st.integers(0, n - 1), min_size=e, max_size=e))
+    dst = draw(st.lists(st.integers(0, n - 1), min_size=e, max_size=e))
+    return n, np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64)
+
+
+@settings(max_examples=60, deadline=None)
+@given(_multigraphs())
+def test_native_csr_is_a_stable_sort_on_any_multigraph(gr):
+    n, src, dst = gr
+    ix = Graph(src, dst, n).index
+    for key, ptr, eid in ((dst, ix.in_ptr.numpy(), ix.in_eid.numpy()), (src, ix.out_ptr.numpy(), ix.out_eid.numpy())):
+        assert np.array_equal(eid, np.argsort(key, kind="stable"))
+        assert np.array_equal(ptr, np.concatenate([[0], np.cumsum(np.bincount(key, minlength=n))]))
+    assert ix.dst_sorted == bool(np.all(np.diff(dst) >= 0))
+    assert ix.max_in_deg == (int(np.bincount(dst, minlength=n).max()) if dst.size else 0)
+
+
+@settings(max_examples=60, deadline=None)
+@given(_multigraphs())
+def test_native_line_graph_is_the_definition_on_any_multigraph(gr):
+    """L(g) has an edge i -> j exactly when dst(i) == src(j) and i != j (DGL line_graph with backtracking; graphs.py:588);
+    emitted destination-major with ascending sources."""
+    n, src, dst = gr
+    lg = Graph(src, dst, n).line_graph()
+    want = [(i, j) for j in range(src.size) for i in range(src.size) if dst[i] == src[j] and i != j]
+    ls, lt = (a.numpy() for a in lg.edges())
+    assert list(zip(ls.tolist(), lt.tolist())) == want
+    assert lg.num_nodes() == src.size
