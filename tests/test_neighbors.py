@@ -71,3 +71,33 @@ def test_knn_graph_on_diamond_gives_first_two_shells():
     assert deg.min() >= 12 and deg.max() <= 16
     d = np.linalg.norm(r, axis=1)
     assert np.allclose(np.unique(np.round(d, 3)), [2.352, 3.840])
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_radius_graph_is_invariant_under_rigid_translation_and_atom_relabelling(seed):
+    """Size-independent properties of the periodic neighbour search: the multiset of bond lengths does not change when
+    the crystal is translated rigidly, and relabelling atoms only relabels bonds."""
+    lat, X = _random_cell(seed, 6)
+    _, _, r0, _ = neighbors.radius_graph(lat, X, cutoff=4.0)
+    base = np.sort(np.round(np.linalg.norm(r0, axis=1), 5))
+    shift = np.array([0.37, -1.2, 2.9])
+    _, _, r1, _ = neighbors.radius_graph(lat, X + shift, cutoff=4.0)
+    assert np.array_equal(np.sort(np.round(np.linalg.norm(r1, axis=1), 5)), base)
+    perm = np.random.default_rng(seed).permutation(6)
+    u2, v2, r2, _ = neighbors.radius_graph(lat, X[perm], cutoff=4.0)
+    assert np.array_equal(np.sort(np.round(np.linalg.norm(r2, axis=1), 5)), base)
+    # bond (u, v) of the relabelled crystal joins the original atoms (perm[u], perm[v]): displacement = image offset apart
+    d = (X[perm][v2] - X[perm][u2]) - r2
+    frac = d @ np.linalg.inv(lat)
+    assert np.allclose(frac, np.round(frac), atol=1e-5)
+
+
+def test_crystal_graph_with_the_k_nearest_strategy_builds_graph_and_line_graph():
+    lat, X = neighbors.diamond_supercell(reps=2, jitter=0.02, seed=1)
+    g, lg = neighbors.crystal_graph(lat, X, torch.zeros(64, 92), cutoff=8.0, neighbor_strategy="k-nearest", max_neighbors=12)
+    s, t = (a.long() for a in g.edges())
+    assert torch.equal(s[0::2], t[1::2]) and torch.equal(t[0::2], s[1::2])       # (u, v) then (v, u), graphs.py:253-257
+    assert int(torch.bincount(t, minlength=64).min()) >= 12
+    assert lg.num_nodes() == g.num_edges() and lg.index.dst_sorted
+    with pytest.raises(ValueError):
+        neighbors.crystal_graph(lat, X, torch.zeros(64, 92), neighbor_strategy="voronoi")
