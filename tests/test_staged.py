@@ -325,3 +325,82 @@ def test_device_radius_scan_bit_identical_to_host_scan(staged, reps, jitter):
     assert np.array_equal(du.cpu().numpy(), u) and np.array_equal(dv.cpu().numpy(), v)
     assert np.array_equal(cells[dc.cpu().numpy()], cells_of_bond)
     assert np.array_equal(dr.cpu().numpy(), r)
+
+
+# ---- thread-level restatement of the fused kernel's epilogue index arithmetic -------------------------------------------
+def _emulate_threads(tiles, in_ptr, in_eid, src, dst, y, W, b, P, D, EG, eps=1e-6):
+    """Python transcription of the epilogue of egc_fused_tc.cu at thread granularity (same formulas for et / col / rg /
+    chunk ownership / staging strides / stat slots), with the GEMM done by numpy.  Catches index-arithmetic mistakes
+    that the tile-level emulation above cannot see."""
+    BM, GT = 128, 128
+    CC = 32 // EG
+    NG = GT // CC
+    STG = CC + 4
+    Nn = in_ptr.size - 1
+    M = np.full_like(y, np.nan)
+    S, H, XP = (np.full((Nn, D), np.nan) for _ in range(3))
+    stat = np.zeros((NG, 2, D))
+    for v0, nseg, p0, rows in tiles:
+        acc = np.zeros((BM, D))
+        if rows:
+            acc[:rows] = y[in_eid[p0:p0 + rows]] @ W.T
+        for grp in range(EG):
+            seg = np.zeros(BM + 1, dtype=np.int64)
+            for et in range(GT):                                     # seg[] fill, one entry per thread (+1 by thread 0)
+                if et <= nseg:
+                    seg[et] = in_ptr[v0 + et] - p0
+                if et == 0 and nseg == BM:
+                    seg[BM] = in_ptr[v0 + BM] - p0
+            for c0 in range(grp * CC, D, EG * CC):
+                stg = np.full((3, BM * STG), np.nan)
+                for et in range(GT):                                 # row phase: thread = tile row
+                    if et < rows:
+                        e = in_eid[p0 + et]
+                        s_, t_ = src[e], dst[e]
+                        v = (acc[et, c0:c0 + CC] + b[c0:c0 + CC]) + (P[s_, c0:c0 + CC] + P[t_, 2 * D + c0:2 * D + c0 + CC])
+                        M[e, c0:c0 + CC] = v
+                        stg[2, et * STG:et * STG + CC] = v
+                        stg[0, et * STG:et * STG + CC] = 1.0 / (1.0 + np.exp(-v))
+                        stg[1, et * STG:et * STG + CC] = P[s_, D + c0:D + c0 + CC]
+                    else:
+                        stg[2, et * STG:et * STG + CC] = 0.0
+                for et in range(GT):                                 # column phase: thread = (column, row group)
+                    col, rg = et % CC, et // CC
+                    for j in range(rg, nseg, NG):
+                        vtx = v0 + j
+                        s1 = s2 = 0.0
+                        for r in range(seg[j], seg[j + 1]):
+                            g_ = stg[0, r * STG + col]
+                            s1 += g_
+                            s2 += stg[1, r * STG + col] * g_
+                        h = s2 / (s1 + eps)
+                        XP[vtx, c0 + col] = P[vtx, 3 * D + c0 + col] + h
+                        S[vtx, c0 + col], H[vtx, c0 + col] = s1, h
+                    x = stg[2, [r * STG + col for r in range(rg * (BM // NG), (rg + 1) * (BM // NG))]]
+                    stat[rg, 0, c0 + col] += x.sum()
+                    stat[rg, 1, c0 + col] += (x * x).sum()
+    return M, S, H, XP, stat.sum(0)
+
+
+@pytest.mark.parametrize("EG", [1, 2])
+def test_thread_level_restatement_agrees_with_tile_level_data_flow(staged, EG):
+    g, lg, _, _ = synthetic.make_batch(batch_size=2, atoms=5, k=12, seed=9, vary_atoms=True)
+    rng = np.random.default_rng(3)
+    D = 64
+    for gr in (g, lg):
+        s, t = (a.numpy() for a in gr.edges())
+        perm = rng.permutation(s.size)
+        gr2 = Graph(s[perm], t[perm], gr.num_nodes())
+        ix = gr2.index
+        Nn, Ne = gr2.num_nodes(), gr2.num_edges()
+        y, W, b = rng.normal(size=(Ne, D)), rng.normal(size=(D, D)) / 8, rng.normal(size=D)
+        P = rng.normal(size=(Nn, 4 * D))
+        n, tiles = pack_tiles(staged, ix.in_ptr.numpy())
+        args = (tiles, ix.in_ptr.numpy().astype(np.int64), ix.in_eid.numpy().astype(np.int64), ix.src.numpy().astype(np.int64),
+                ix.dst.numpy().astype(np.int64), y, W, b, P)
+        ref = _emulate(*args)
+        out = _emulate_threads(*args, D, EG)
+        for a_, b_, name in zip(out, ref, ("M", "S", "H", "XP")):
+            assert not np.isnan(a_).any(), name                      # every element written exactly by some thread
+            np.testing.assert_allclose(a_, b_, rtol=1e-12, atol=1e-12, err_msg=name)
+        np.testing.assert_allclose(out[4], ref[4], rtol=1e-10, atol=1e-9)
