@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--mode", choices=["stats", "affine", "layer"], default="stats")
     ap.add_argument("--groups", type=int, choices=[1, 2], default=1, help="epilogue groups of the fused kernel")
+    ap.add_argument("--graphs", default="g,lg", help="which of the two graphs to time (comma separated: g, lg)")
     args = ap.parse_args()
     import staged_binding as SB
     from alignn_b200 import ops, synthetic
@@ -34,6 +35,8 @@ def main():
     res = {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for name, gr in (("g", g), ("lg", lg)):
+        if name not in args.graphs.split(","):
+            continue
         grd = gr.to(dev)
         ix = grd.index
         Nn, Ne = gr.num_nodes(), gr.num_edges()

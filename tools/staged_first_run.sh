@@ -27,7 +27,7 @@ if [ $rc -eq 0 ]; then
   #    the replay passes cost seconds, not minutes)
   for groups in 1 2; do
     timeout 300 ncu --set full --clock-control none --import-source on -k regex:egc_forward_fused -c 1 \
-      -o gpurun_out/staged_fused_g${groups} -f python tools/bench_fused.py --mode stats --groups $groups --iters 2 \
+      -o gpurun_out/staged_fused_g${groups} -f python tools/bench_fused.py --mode stats --groups $groups --iters 2 --graphs lg \
       > gpurun_out/staged_ncu_g${groups}.log 2>&1
     echo "ncu groups=$groups: exit $?"
   done
