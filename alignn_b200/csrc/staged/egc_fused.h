@@ -60,6 +60,42 @@ int alignn_b200_ln_silu_residual(const float* R, const float* res, const float* 
                                  float* out, int64_t n, int d, void* stream);
 int alignn_b200_staged_last_cuda_error(void);
 
+/* ---- backward, train-mode BatchNorm (ALIGNN_NORM_STATS) only -------------------------------------------------------
+ * Node side (small, [Nn,d] rows): dL/dx' through the node BatchNorm + SiLU, and the two per-node factors the edge
+ * side needs:  GPD = dL/dx' (goes to GP[:, 3d:4d]),  GSh = dL/dSh = dL/dx' / (S + eps),
+ * GS = dL/dS = -dL/dx' * h / (S + eps);  partials [rows][d] = column sums of dL/dx' (bias gradient of src_update).
+ * n_w / n_b = scale / shift of the batch statistics, n_c1 / n_c2 from alignn_b200_bn_backward_reduce. */
+int alignn_b200_egc_backward_nodes(const float* XP, const float* gx_out, const float* S, const float* H, const float* n_w,
+                                   const float* n_b, const float* n_mean, const float* n_rstd, const float* n_c1,
+                                   const float* n_c2, float gate_eps, int64_t Nn, int d, float* GPD, int64_t ld_gpd,
+                                   float* GSh, float* GS, float* partials, int partial_rows, void* stream);
+
+/* Edge side in ONE tcgen05 kernel: the producer warps form  gm = dL/dm  per element from M, gy_out and the gathered
+ * P[src, d:2d], GSh[dst], GS[dst] rows (BatchNorm + SiLU backward, gate backward), write GM and feed the bf16 hi/lo
+ * split of the same values to the tensor cores;  gy = GM * W_eg (+ gy_out) leaves through the epilogue, which also
+ * sums GM over every destination segment (GPB = GP[:, 2d:3d] = dL/d e_dst) -- i.e. egc_backward_dst_kernel's edge
+ * loop and the data-gradient GEMM of alignn/models/alignn.py:101 in one pass over M and gy_out.
+ * Same segment-aligned tiles as the forward kernel.  gy_out == NULL: dead edge output (no norm term, no residual). */
+typedef struct {
+  size_t struct_size;
+  int64_t Nn, Ne;
+  int32_t d;
+  int32_t residual;
+  const float* M; const float* gy_out;
+  const float* P; const float* GSh; const float* GS;
+  const void* w_image;   /* alignn_b200_gemm_prepare_weights(W_eg, N=d, K=d, transpose=1) */
+  const int32_t* src; const int32_t* dst; const int32_t* in_ptr; const int32_t* in_eid;
+  const int32_t* tiles; int32_t num_tiles;
+  const float* e_w; const float* e_b; const float* e_mean; const float* e_rstd; const float* e_c1; const float* e_c2;
+  float* GM;             /* [Ne,d] */
+  float* gy;             /* [Ne,d] or NULL */
+  float* GPB; int64_t ld_gpb;   /* dL/d e_dst rows, e.g. GP + 2d with ld 4d */
+  float* partials;       /* [min(num_tiles,148)][d] column sums of gm (= bias gradients of edge_gate and dst_gate) */
+  void* stream;
+} alignn_b200_egc_bwd_fused_args;
+
+int alignn_b200_egc_backward_fused(const alignn_b200_egc_bwd_fused_args* args);
+
 #ifdef __cplusplus
 }
 #endif

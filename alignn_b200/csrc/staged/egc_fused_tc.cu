@@ -37,7 +37,7 @@ constexpr uint32_t LBO = 128;
 constexpr uint32_t SBO = (BK / 8) * 128;
 constexpr int kSMs = 148;
 
-static std::atomic<int> g_last_cuda_error{0};
+std::atomic<int> g_last_cuda_error{0};   // shared with egc_bwd_fused_tc.cu
 
 // EG = number of epilogue groups.  With two groups the column chunks alternate between them, so one group's row
 // phase (L2 gathers, MUFU) overlaps the other's column phase; chunks are then 16 columns wide to keep the staging

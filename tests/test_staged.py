@@ -60,6 +60,13 @@ def test_ctypes_struct_matches_staged_header(staged):
     assert staged.alignn_b200_egc_forward_fused(C.byref(a)) == 0
     a.struct_size += 8
     assert staged.alignn_b200_egc_forward_fused(C.byref(a)) != 0
+    staged.alignn_b200_egc_backward_fused.restype = C.c_int
+    b = staged_binding.BwdFusedArgs(struct_size=C.sizeof(staged_binding.BwdFusedArgs), Nn=0, Ne=0, d=64, residual=1)
+    assert staged.alignn_b200_egc_backward_fused(C.byref(b)) == 0
+    b.d = 32                                   # the fused backward keeps d = 32 on the two-kernel path
+    assert staged.alignn_b200_egc_backward_fused(C.byref(b)) != 0
+    b.d, b.struct_size = 64, b.struct_size + 8
+    assert staged.alignn_b200_egc_backward_fused(C.byref(b)) != 0
 
 
 def test_tile_packer_rejects_oversized_segment(staged):
@@ -404,3 +411,59 @@ def test_thread_level_restatement_agrees_with_tile_level_data_flow(staged, EG):
             assert not np.isnan(a_).any(), name                      # every element written exactly by some thread
             np.testing.assert_allclose(a_, b_, rtol=1e-12, atol=1e-12, err_msg=name)
         np.testing.assert_allclose(out[4], ref[4], rtol=1e-10, atol=1e-9)
+
+
+@pytest.mark.gpu
+@needs_optin
+@pytest.mark.parametrize("dead_edge_out", [False, True])
+@pytest.mark.parametrize("d", [256, 64])
+def test_fused_backward_matches_shipped_backward(staged, d, dead_edge_out):
+    """Node kernel + fused edge kernel (gm, GM, segment sums, gy = GM W_eg + gy_out) against `ops.egc_backward` followed
+    by the shipped data-gradient GEMM, train-mode BatchNorm, on g and L(g) with permuted edge order."""
+    import staged_binding
+    from alignn_b200 import ops
+    dev = torch.device("cuda:0")
+    g, lg, _, _ = synthetic.make_batch(batch_size=4, atoms=9, k=12, seed=19, vary_atoms=True)
+    for gr in (g, lg):
+        s_, t_ = (a.numpy() for a in gr.edges())
+        perm = np.random.default_rng(6).permutation(s_.size)
+        grd = Graph(s_[perm], t_[perm], gr.num_nodes()).to(dev)
+        ix = grd.index
+        Nn, Ne = gr.num_nodes(), gr.num_edges()
+        gen = torch.Generator().manual_seed(11)
+        rnd = lambda *s: torch.randn(*s, generator=gen).to(dev)  # noqa: E731
+        x, y, gx_out, gy_out = rnd(Nn, d), rnd(Ne, d), rnd(Nn, d), rnd(Ne, d)
+        Wcat, W_eg = rnd(4 * d, d) / d ** 0.5, rnd(d, d) / d ** 0.5
+        bcat, b_eg = rnd(4 * d), rnd(d)
+        P = ops.gemm_nt(x, ops.WeightImage(Wcat), bcat)
+        G = ops.gemm_nt(y, ops.WeightImage(W_eg), b_eg)
+        ones = torch.ones(d, device=dev)
+        fwd = ops.egc_forward(ix, x, y, G, P, None, None, None, None, norm_nodes=ops.NORM_STATS, norm_edges=ops.NORM_STATS,
+                              residual=True, save=True, need_edge_out=True)
+        n_aux = ops.bn_finalize(fwd["partials"], 1, Nn, ones, 0 * ones, 1e-5, 0.1, None, None)
+        e_aux = ops.bn_finalize(fwd["partials"], 0, Ne, ones, 0 * ones, 1e-5, 0.1, None, None)
+        nd = dict(w=n_aux[0], b=n_aux[1], mean=n_aux[2], rstd=n_aux[3])
+        ed = dict(w=e_aux[0], b=e_aux[1], mean=e_aux[2], rstd=e_aux[3])
+        nd["c1"], nd["c2"] = ops.bn_backward_reduce(fwd["XP"], gx_out, *n_aux)
+        go = None if dead_edge_out else gy_out
+        if go is not None:
+            ed["c1"], ed["c2"] = ops.bn_backward_reduce(fwd["M"], go, *e_aux)
+        GM, GP, vd, _ = ops.egc_backward(ix, P, fwd["M"], fwd["XP"], fwd["S"], fwd["H"], gx_out, go, nd, ed if go is not None else {},
+                                         norm_nodes=ops.NORM_STATS, norm_edges=ops.NORM_STATS)
+        img_t = ops.WeightImage(W_eg, transpose=True)
+        gy_ref = ops.gemm_nt(GM, img_t, None, go)
+        n, tiles = pack_tiles(staged, ix.in_ptr.cpu().numpy())
+        tiles_d = torch.from_numpy(tiles).to(dev)
+        out = staged_binding.backward_fused(staged, ix, tiles_d, n, P, fwd["M"], fwd["XP"], fwd["S"], fwd["H"], gx_out, go, nd, ed,
+                                            img_t)
+        torch.cuda.synchronize()
+
+        def close(a_, b_, what, tol=2e-5):
+            err = (a_ - b_).abs().max().item()
+            assert err <= tol * max(b_.abs().max().item(), 1e-6), (what, err, b_.abs().max().item())
+        close(out["GM"], GM, "GM")
+        close(out["GP"][:, 2 * d:3 * d], GP[:, 2 * d:3 * d], "GP e_dst")
+        close(out["GP"][:, 3 * d:], GP[:, 3 * d:], "GP src_update")
+        close(out["sum_gD"], vd[4], "sum dL/dx'", 1e-4)
+        close(out["sum_gm"], vd[5], "sum gm", 1e-4)
+        close(out["gy"], gy_ref, "gy", 1e-4)      # the fused GEMM consumes the same gm to within the rounding of gm itself

@@ -226,3 +226,53 @@ def radius_scan_device(lib, X, shifts, cutoff, atol=1e-5):
     if rc != 0:
         raise RuntimeError(f"alignn_b200_radius_graph_fill -> {rc}")
     return u, v, c, r
+
+
+# ---- fused backward (csrc/staged/egc_bwd_fused_tc.cu + node side in node_tail.cu) ----------------------------------
+class BwdFusedArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_size_t), ("Nn", C.c_int64), ("Ne", C.c_int64), ("d", C.c_int32), ("residual", C.c_int32),
+                ("M", C.c_void_p), ("gy_out", C.c_void_p), ("P", C.c_void_p), ("GSh", C.c_void_p), ("GS", C.c_void_p),
+                ("w_image", C.c_void_p), ("src", C.c_void_p), ("dst", C.c_void_p), ("in_ptr", C.c_void_p), ("in_eid", C.c_void_p),
+                ("tiles", C.c_void_p), ("num_tiles", C.c_int32),
+                ("e_w", C.c_void_p), ("e_b", C.c_void_p), ("e_mean", C.c_void_p), ("e_rstd", C.c_void_p), ("e_c1", C.c_void_p),
+                ("e_c2", C.c_void_p), ("GM", C.c_void_p), ("gy", C.c_void_p), ("GPB", C.c_void_p), ("ld_gpb", C.c_int64),
+                ("partials", C.c_void_p), ("stream", C.c_void_p)]
+
+
+def backward_fused(lib, ix, tiles_d, n_tiles, P, M, XP, S, H, gx_out, gy_out, n, e, W_eg_T_img, residual=True, need_gy=True):
+    """Train-mode BatchNorm backward of one conv up to (GM, GP[:, 2d:4d], gy, column sums): node kernel + fused edge
+    kernel.  n / e: dicts with w, b, mean, rstd, c1, c2 (as for `ops.egc_backward`).  GP[:, 0:2d] (the source-keyed
+    sums) is NOT produced here: it still comes from egc_backward_src_kernel."""
+    import torch
+    from alignn_b200 import ops
+    from alignn_b200._lib import ptr, stream_ptr
+    lib.alignn_b200_egc_backward_nodes.restype = C.c_int
+    lib.alignn_b200_egc_backward_nodes.argtypes = [C.c_void_p] * 10 + [C.c_float, C.c_int64, C.c_int, C.c_void_p, C.c_int64,
+                                                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.alignn_b200_egc_backward_fused.restype = C.c_int
+    lib.alignn_b200_egc_backward_fused.argtypes = [C.POINTER(BwdFusedArgs)]
+    Nn, d = XP.shape
+    Ne = M.shape[0]
+    dev = XP.device
+    new = lambda *s: torch.full(s, float("nan"), device=dev, dtype=torch.float32)  # noqa: E731
+    GP, GSh, GS, GM = new(Nn, 4 * d), new(Nn, d), new(Nn, d), new(Ne, d)
+    gy = new(Ne, d) if need_gy else None
+    rows_n = ops.partial_rows(Nn, d)
+    part_n = new(rows_n, d)
+    rc = lib.alignn_b200_egc_backward_nodes(ptr(XP), ptr(gx_out), ptr(S), ptr(H), ptr(n["w"]), ptr(n["b"]), ptr(n["mean"]),
+                                            ptr(n["rstd"]), ptr(n["c1"]), ptr(n["c2"]), 1e-6, Nn, d,
+                                            GP.data_ptr() + 3 * d * 4, 4 * d, ptr(GSh), ptr(GS), ptr(part_n), rows_n, stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"alignn_b200_egc_backward_nodes -> {rc}")
+    rows_e = lib.alignn_b200_egc_fused_partial_rows(n_tiles)
+    part_e = new(rows_e, d)
+    g = lambda k: ptr(e.get(k)) if gy_out is not None else None  # noqa: E731
+    a = BwdFusedArgs(struct_size=C.sizeof(BwdFusedArgs), Nn=Nn, Ne=Ne, d=d, residual=int(residual), M=ptr(M), gy_out=ptr(gy_out),
+                     P=ptr(P), GSh=ptr(GSh), GS=ptr(GS), w_image=ops.ptr_any(W_eg_T_img.buf), src=ptr(ix.src), dst=ptr(ix.dst),
+                     in_ptr=ptr(ix.in_ptr), in_eid=None if ix.dst_sorted else ptr(ix.in_eid), tiles=ptr(tiles_d),
+                     num_tiles=n_tiles, e_w=g("w"), e_b=g("b"), e_mean=g("mean"), e_rstd=g("rstd"), e_c1=g("c1"), e_c2=g("c2"),
+                     GM=ptr(GM), gy=ptr(gy), GPB=GP.data_ptr() + 2 * d * 4, ld_gpb=4 * d, partials=ptr(part_e), stream=stream_ptr())
+    rc = lib.alignn_b200_egc_backward_fused(C.byref(a))
+    if rc != 0:
+        raise RuntimeError(f"alignn_b200_egc_backward_fused -> {rc} (cuda error {lib.alignn_b200_staged_last_cuda_error()})")
+    return dict(GM=GM, GP=GP, GSh=GSh, gy=gy, sum_gD=part_n.sum(0), sum_gm=part_e.sum(0))

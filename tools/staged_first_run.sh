@@ -12,9 +12,12 @@ python tools/build_staged.py > gpurun_out/staged_build.log 2>&1 || { echo "stage
 timeout 300 python -m pytest tests/test_staged.py -m gpu -x -q -k "device" > gpurun_out/staged_device_tests.log 2>&1
 echo "device builders: exit $?"; tail -3 gpurun_out/staged_device_tests.log
 # 2. the fused forward, smallest configuration first
-timeout 300 python -m pytest tests/test_staged.py -m gpu -x -q -k "fused" > gpurun_out/staged_fused_tests.log 2>&1
+timeout 300 python -m pytest tests/test_staged.py -m gpu -x -q -k "fused and not backward" > gpurun_out/staged_fused_tests.log 2>&1
 rc=$?
 echo "fused forward: exit $rc"; tail -15 gpurun_out/staged_fused_tests.log
+# 2b. the fused backward (independent of the forward kernel's result)
+timeout 300 python -m pytest tests/test_staged.py -m gpu -x -q -k "fused_backward" > gpurun_out/staged_bwd_tests.log 2>&1
+echo "fused backward: exit $?"; tail -15 gpurun_out/staged_bwd_tests.log
 # 3. timing only if it is correct
 if [ $rc -eq 0 ]; then
   for mode in stats affine layer; do
