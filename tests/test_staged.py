@@ -467,3 +467,19 @@ def test_fused_backward_matches_shipped_backward(staged, d, dead_edge_out):
         close(out["sum_gD"], vd[4], "sum dL/dx'", 1e-4)
         close(out["sum_gm"], vd[5], "sum gm", 1e-4)
         close(out["gy"], gy_ref, "gy", 1e-4)      # the fused GEMM consumes the same gm to within the rounding of gm itself
+
+
+def test_folded_batchnorm_backward_constants_are_the_same_function():
+    """egc_bwd_fused_tc.cu folds  w (c1 + xhat c2),  xhat = (m - mean) rstd,  into  A + B m  with  B = w c2 rstd,
+    A = w c1 - B mean: same function of m as norm_backward_row of the shipped kernel."""
+    rng = np.random.default_rng(0)
+    m, go = rng.normal(size=(50, 16)), rng.normal(size=(50, 16))
+    w, b, mean, c1, c2 = (rng.normal(size=16) for _ in range(5))
+    rstd = rng.random(16) + 0.5
+    sig = lambda x: 1 / (1 + np.exp(-x))  # noqa: E731
+    u = m * w + b
+    gu = go * (sig(u) * (1 + u * (1 - sig(u))))
+    shipped = w * gu - w * (c1 + (m - mean) * rstd * c2)
+    B = w * c2 * rstd
+    A = w * c1 - B * mean
+    np.testing.assert_allclose(w * gu - (A + B * m), shipped, rtol=1e-12, atol=1e-12)
