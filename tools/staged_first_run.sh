@@ -17,7 +17,11 @@ rc=$?
 echo "fused forward: exit $rc"; tail -15 gpurun_out/staged_fused_tests.log
 # 2b. the fused backward (independent of the forward kernel's result)
 timeout 300 python -m pytest tests/test_staged.py -m gpu -x -q -k "fused_backward" > gpurun_out/staged_bwd_tests.log 2>&1
-echo "fused backward: exit $?"; tail -15 gpurun_out/staged_bwd_tests.log
+rcb=$?
+echo "fused backward: exit $rcb"; tail -15 gpurun_out/staged_bwd_tests.log
+if [ $rcb -eq 0 ]; then
+  timeout 300 python tools/bench_fused_bwd.py >> gpurun_out/staged_bench_fused.jsonl 2>> gpurun_out/staged_bench_fused.err
+fi
 # 3. timing only if it is correct
 if [ $rc -eq 0 ]; then
   for mode in stats affine layer; do
