@@ -67,7 +67,8 @@ def step_bytes(N, E, T, d, n_alignn, n_gcn):
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        j = json.load(open(p))
+        with open(p) as fh:
+            j = json.load(fh)
         return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
