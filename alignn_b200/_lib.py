@@ -27,6 +27,7 @@ class EgcFwdArgs(C.Structure):
         ("struct_size", C.c_size_t),
         ("Nn", C.c_int64), ("Ne", C.c_int64),
         ("d", C.c_int32), ("norm_nodes", C.c_int32), ("norm_edges", C.c_int32), ("residual", C.c_int32),
+        ("gate_is_m", C.c_int32),
         ("gate_eps", C.c_float), ("ln_eps", C.c_float),
         ("x", _fp), ("y", _fp), ("G", _fp), ("P", _fp),
         ("src", _fp), ("in_ptr", _fp), ("in_eid", _fp),
@@ -55,6 +56,20 @@ class EgcBwdArgs(C.Structure):
     ]
 
 
+class GemmGatherArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_size_t),
+        ("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32),
+        ("A", _fp), ("lda", C.c_int64),
+        ("w_image", _fp), ("bias", _fp),
+        ("add0", _fp), ("ld0", C.c_int64), ("idx0", _fp),
+        ("add1", _fp), ("ld1", C.c_int64), ("idx1", _fp),
+        ("C", _fp), ("ldc", C.c_int64),
+        ("stats", _fp),
+        ("stream", _fp),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/alignn_b200.h one to one
 _SIGNATURES = {
     "alignn_b200_version": (C.c_int, []),
@@ -77,6 +92,8 @@ _SIGNATURES = {
     "alignn_b200_gemm_prepare_weights": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int64, C.c_int, _fp, _fp]),
     "alignn_b200_gemm_nt": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, C.c_int, C.c_int, _fp, _fp, C.c_int64, _fp,
                                       C.c_int64, _fp]),
+    "alignn_b200_gemm_gather": (C.c_int, [C.POINTER(GemmGatherArgs)]),
+    "alignn_b200_gemm_gather_stat_rows": (C.c_int, [C.c_int64, C.c_int]),
     "alignn_b200_wgrad_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int, C.c_int]),
     "alignn_b200_wgrad": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _fp, C.c_int64,
                                     _fp, C.c_size_t, _fp]),

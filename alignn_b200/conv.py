@@ -16,6 +16,8 @@ it is reached through the C ABI (include/alignn_b200.h).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 from torch.autograd.function import once_differentiable
@@ -25,6 +27,9 @@ from .graph import as_graph
 from .ops import NORM_AFFINE, NORM_LAYER, NORM_STATS
 
 GATE_EPS = 1e-6   # alignn.py:109
+# True: pass 1 = TMA-fed gather GEMM writes m and its batch statistics, pass 2 = segment reductions + edge tail.
+# False: the round-1 composition (plain GEMM writes G, the edge kernel forms m); kept for A/B runs and bit-identity tests.
+USE_GATHER_GEMM = os.environ.get("ALIGNN_B200_GATHER_GEMM", "1") != "0"
 
 
 class _Cfg:
@@ -61,42 +66,74 @@ class _EdgeGatedConvFn(torch.autograd.Function):
         Nn, d = x.shape
         Ne = y.shape[0]
         needs_grad = any(ctx.needs_input_grad)
-        # node projections P = [e_src | Bh | e_dst | src_update] (include/alignn_b200.h) and edge gate G
-        # (tcgen05 bf16x3 GEMMs, csrc/gemm_tc.cu; weights are re-split every call because they change every step)
-        Wcat = torch.cat([W_sg, W_du, W_dg, W_su], 0)
-        bcat = torch.cat([b_sg, b_du, b_dg, b_su], 0)
-        P = ops.gemm_nt(x, ops.WeightImage(Wcat), bcat)
-        G = ops.gemm_nt(y, ops.WeightImage(W_eg.contiguous()), b_eg.contiguous())
-
+        stats = cfg.norm_nodes == NORM_STATS
         n_aux = e_aux = None
         if cfg.norm_nodes == NORM_AFFINE:
             n_aux = _bn_eval_vectors(cfg.bn_nodes)
             e_aux = _bn_eval_vectors(cfg.bn_edges)
             n_w, n_b, e_w, e_b = n_aux[0], n_aux[1], e_aux[0], e_aux[1]
-        elif cfg.norm_nodes == NORM_STATS:
+        elif stats:
             n_w = n_b = e_w = e_b = None
         else:
             n_w, n_b, e_w, e_b = nw.contiguous(), nb.contiguous(), ew.contiguous(), eb.contiguous()
+        bnn, bne = cfg.bn_nodes, cfg.bn_edges
 
-        out = ops.egc_forward(ix, x, y, G, P, n_w, n_b, e_w, e_b, norm_nodes=cfg.norm_nodes,
-                              norm_edges=cfg.norm_edges, residual=cfg.residual, save=needs_grad,
-                              need_edge_out=cfg.need_edge_out, gate_eps=GATE_EPS, ln_eps=cfg.ln_eps)
-        x_out, y_out = out["x_out"], out["y_out"]
-        if cfg.norm_nodes == NORM_STATS:
-            # BatchNorm1d train mode (alignn.py:122-123): batch statistics, running-stat update
-            bnn, bne = cfg.bn_nodes, cfg.bn_edges
-            track_n = bnn.track_running_stats and bnn.running_mean is not None
-            track_e = bne.track_running_stats and bne.running_mean is not None
-            n_aux = ops.bn_finalize(out["partials"], 1, Nn, nw, nb, bnn.eps, _momentum(bnn),
-                                    bnn.running_mean if track_n else None, bnn.running_var if track_n else None)
-            x_out = ops.affine_silu_residual(out["XP"], x if cfg.residual else None, n_aux[0], n_aux[1])
+        # node projections P = [e_src | Bh | e_dst | src_update] (include/alignn_b200.h); the edge-gate bias rides in
+        # the e_dst block, so the gate needs no bias of its own (weights are re-split every call: they change every step)
+        Wcat = torch.cat([W_sg, W_du, W_dg, W_su], 0)
+        if USE_GATHER_GEMM:
+            bcat = torch.cat([b_sg, b_du, b_dg + b_eg, b_su], 0)
+            P = ops.gemm_gather(x, ops.WeightImage(Wcat), bcat)
+            # pass 1 over the edge rows (csrc/gemm_fused_tc.cu): m = e_src[src] + e_dst[dst] + edge_gate(y) on tcgen05,
+            # y streamed by TMA, the P rows gathered in the epilogue, BatchNorm batch statistics of m on the way out
+            e_part = None
             if Ne > 0:
+                res = ops.gemm_gather(y, ops.WeightImage(W_eg.contiguous()), None, add0=P[:, 0:d], idx0=ix.src,
+                                      add1=P[:, 2 * d:3 * d], idx1=ix.dst, stats=stats)
+                M, e_part = res if stats else (res, None)
+            else:
+                M = y.new_empty((0, d))
+            norm_e = cfg.norm_edges
+            if stats and Ne > 0:
                 # statistics (and running buffers) are updated even when the edge output is dead
                 # (SURVEY.md App. D-11): the reference always evaluates bn_edges(m).
-                e_aux = ops.bn_finalize(out["partials"], 0, Ne, ew, eb, bne.eps, _momentum(bne),
+                track_e = bne.track_running_stats and bne.running_mean is not None
+                e_aux = ops.bn_finalize(e_part, 0, Ne, ew, eb, bne.eps, _momentum(bne),
                                         bne.running_mean if track_e else None, bne.running_var if track_e else None)
-                if cfg.need_edge_out:
-                    y_out = ops.affine_silu_residual(out["M"], y if cfg.residual else None, e_aux[0], e_aux[1])
+                e_w, e_b = e_aux[0], e_aux[1]
+            if stats:
+                norm_e = NORM_AFFINE
+            # pass 2 (csrc/egc_kernels.cu): sigmoid, both segment reductions by sorted-CSR index, y_out = y + silu(norm(m))
+            out = ops.egc_forward(ix, x, y, M, P, n_w, n_b, e_w, e_b, norm_nodes=cfg.norm_nodes, norm_edges=norm_e,
+                                  residual=cfg.residual, save=needs_grad, need_edge_out=cfg.need_edge_out and Ne > 0,
+                                  gate_eps=GATE_EPS, ln_eps=cfg.ln_eps, gate_is_m=True)
+            x_out, y_out = out["x_out"], out["y_out"]
+            if stats:
+                track_n = bnn.track_running_stats and bnn.running_mean is not None
+                n_aux = ops.bn_finalize(out["partials"], 1, Nn, nw, nb, bnn.eps, _momentum(bnn),
+                                        bnn.running_mean if track_n else None, bnn.running_var if track_n else None)
+                x_out = ops.affine_silu_residual(out["XP"], x if cfg.residual else None, n_aux[0], n_aux[1])
+        else:
+            bcat = torch.cat([b_sg, b_du, b_dg, b_su], 0)
+            P = ops.gemm_nt(x, ops.WeightImage(Wcat), bcat)
+            G = ops.gemm_nt(y, ops.WeightImage(W_eg.contiguous()), b_eg.contiguous())
+            out = ops.egc_forward(ix, x, y, G, P, n_w, n_b, e_w, e_b, norm_nodes=cfg.norm_nodes,
+                                  norm_edges=cfg.norm_edges, residual=cfg.residual, save=needs_grad,
+                                  need_edge_out=cfg.need_edge_out, gate_eps=GATE_EPS, ln_eps=cfg.ln_eps)
+            x_out, y_out = out["x_out"], out["y_out"]
+            if stats:
+                # BatchNorm1d train mode (alignn.py:122-123): batch statistics, running-stat update
+                track_n = bnn.track_running_stats and bnn.running_mean is not None
+                track_e = bne.track_running_stats and bne.running_mean is not None
+                n_aux = ops.bn_finalize(out["partials"], 1, Nn, nw, nb, bnn.eps, _momentum(bnn),
+                                        bnn.running_mean if track_n else None, bnn.running_var if track_n else None)
+                x_out = ops.affine_silu_residual(out["XP"], x if cfg.residual else None, n_aux[0], n_aux[1])
+                if Ne > 0:
+                    e_aux = ops.bn_finalize(out["partials"], 0, Ne, ew, eb, bne.eps, _momentum(bne),
+                                            bne.running_mean if track_e else None, bne.running_var if track_e else None)
+                    if cfg.need_edge_out:
+                        y_out = ops.affine_silu_residual(out["M"], y if cfg.residual else None, e_aux[0], e_aux[1])
+        if stats:
             for bn in (bnn, bne):
                 if bn.track_running_stats and bn.num_batches_tracked is not None:
                     bn.num_batches_tracked.add_(1)

@@ -17,7 +17,10 @@ __device__ __forceinline__ float dsilu_(float u) { float s = sigmoidf_(u); retur
 // =============================================================================================
 // Forward
 // =============================================================================================
-template <int D>
+// GIM ("gate is m"): a.G already holds the pre-activation gate m = e_src[src] + e_dst[dst] + edge_gate(y), written
+// (together with its batch statistics) by the gather GEMM (gemm_fused_tc.cu).  The kernel then neither gathers
+// e_src / e_dst nor writes M nor accumulates edge statistics: it is the second and last pass over the edge rows.
+template <int D, bool GIM>
 __global__ void __launch_bounds__(kThreads, 2)
 egc_forward_kernel(alignn_b200_egc_fwd_args a) {
   using C = RowCfg<D>;
@@ -47,7 +50,7 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
   for (int64_t v = warp0; v < a.Nn; v += nwarps) {
     const int p0 = a.in_ptr[v], p1 = a.in_ptr[v + 1];
     float bv[V], accS[V], accSh[V];
-    ld_row<D, false>(bv, a.P + v * 4 * D + 2 * D, lane);
+    if constexpr (!GIM) ld_row<D, false>(bv, a.P + v * 4 * D + 2 * D, lane);
 #pragma unroll
     for (int i = 0; i < V; ++i) { accS[i] = 0.f; accSh[i] = 0.f; }
 
@@ -66,8 +69,8 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
           accS[k] += sg;
           accSh[k] += cv[k] * sg;
         }
-        if (train) st_row<D, true>(a.M + e * D, m, lane);   // Ne > 0 here, so M is a real buffer
-        if (a.norm_edges == ALIGNN_NORM_STATS) {
+        if (train && !GIM) st_row<D, true>(a.M + e * D, m, lane);   // Ne > 0 here, so M is a real buffer
+        if (!GIM && a.norm_edges == ALIGNN_NORM_STATS) {
           smem_row_add<D>(st, m, lane);
 #pragma unroll
           for (int k = 0; k < V; ++k) m[k] *= m[k];
@@ -101,12 +104,16 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
         float g0[V], a0[V], c0[V], g1[V], a1[V], c1[V];
         ld_row<D, true>(g0, a.G + e0 * D, lane);
         ld_row<D, true>(g1, a.G + e1 * D, lane);
-        ld_row<D, false>(a0, a.P + s0 * 4 * D, lane);
-        ld_row<D, false>(a1, a.P + s1 * 4 * D, lane);
+        if constexpr (!GIM) {
+          ld_row<D, false>(a0, a.P + s0 * 4 * D, lane);
+          ld_row<D, false>(a1, a.P + s1 * 4 * D, lane);
+        }
         ld_row<D, false>(c0, a.P + s0 * 4 * D + D, lane);
         ld_row<D, false>(c1, a.P + s1 * 4 * D + D, lane);
+        if constexpr (!GIM) {
 #pragma unroll
-        for (int k = 0; k < V; ++k) { g0[k] += a0[k] + bv[k]; g1[k] += a1[k] + bv[k]; }
+          for (int k = 0; k < V; ++k) { g0[k] += a0[k] + bv[k]; g1[k] += a1[k] + bv[k]; }
+        }
         edge_tail(e0, g0, c0);
         edge_tail(e1, g1, c1);
       }
@@ -114,10 +121,12 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
         const int64_t e0 = __shfl_sync(0xffffffffu, my_e, i), s0 = __shfl_sync(0xffffffffu, my_s, i);
         float g0[V], a0[V], c0[V];
         ld_row<D, true>(g0, a.G + e0 * D, lane);
-        ld_row<D, false>(a0, a.P + s0 * 4 * D, lane);
+        if constexpr (!GIM) ld_row<D, false>(a0, a.P + s0 * 4 * D, lane);
         ld_row<D, false>(c0, a.P + s0 * 4 * D + D, lane);
+        if constexpr (!GIM) {
 #pragma unroll
-        for (int k = 0; k < V; ++k) g0[k] += a0[k] + bv[k];
+          for (int k = 0; k < V; ++k) g0[k] += a0[k] + bv[k];
+        }
         edge_tail(e0, g0, c0);
       }
     }
@@ -783,12 +792,14 @@ int alignn_b200_egc_forward(const alignn_b200_egc_fwd_args* a) {
                       (a->norm_edges != ALIGNN_NORM_STATS && a->y_out && !a->y))) return ALIGNN_ERR_BAD_ARG;
   if ((a->norm_nodes == ALIGNN_NORM_STATS || a->norm_edges == ALIGNN_NORM_STATS) && !a->partials) return ALIGNN_ERR_BAD_ARG;
   if ((a->norm_nodes == ALIGNN_NORM_STATS || a->norm_edges == ALIGNN_NORM_STATS) && !a->XP) return ALIGNN_ERR_BAD_ARG;
-  if (a->XP && (!a->S || !a->H || (a->Ne > 0 && !a->M))) return ALIGNN_ERR_BAD_ARG;   // training: all saved buffers
+  if (a->XP && (!a->S || !a->H || (a->Ne > 0 && !a->M && !a->gate_is_m))) return ALIGNN_ERR_BAD_ARG;   // training: all saved buffers
+  if (a->gate_is_m && a->norm_edges == ALIGNN_NORM_STATS && a->y_out) return ALIGNN_ERR_BAD_ARG;   // statistics come from the gather GEMM
   cudaStream_t st = (cudaStream_t)a->stream;
   const int grid = grid_for_rows(a->Nn);
   DISPATCH_D(a->d, {
     const size_t smem_bytes = (size_t)(4 + (a->partials ? alignn::kWarpsPerBlock * 4 : 0)) * D * sizeof(float);
-    alignn::egc_forward_kernel<D><<<grid, alignn::kThreads, smem_bytes, st>>>(*a);   // <= 36 KB: no opt-in needed
+    if (a->gate_is_m) alignn::egc_forward_kernel<D, true><<<grid, alignn::kThreads, smem_bytes, st>>>(*a);
+    else alignn::egc_forward_kernel<D, false><<<grid, alignn::kThreads, smem_bytes, st>>>(*a);   // <= 36 KB: no opt-in needed
   });
   return check_launch();
 }

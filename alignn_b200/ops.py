@@ -49,8 +49,12 @@ def partial_rows(num_nodes: int, d: int) -> int:
 
 
 def egc_forward(ix: EdgeIndex, x, y, G, P, n_w, n_b, e_w, e_b, *, norm_nodes: int, norm_edges: int,
-                residual: bool, save: bool, need_edge_out: bool, gate_eps: float = 1e-6, ln_eps: float = 1e-5):
+                residual: bool, save: bool, need_edge_out: bool, gate_eps: float = 1e-6, ln_eps: float = 1e-5,
+                gate_is_m: bool = False):
     """Everything of EdgeGatedGraphConv.forward after the Linear layers (alignn.py:100-127).
+
+    gate_is_m: G already holds the pre-activation gate m (from `gemm_gather` with the e_src / e_dst addends); the
+    kernel then only applies the edge norm / SiLU / residual and reduces the gated messages (second pass over the edges).
 
     Returns dict(x_out, y_out, M, XP, S, H, partials)."""
     lib = _lib.load()
@@ -64,24 +68,27 @@ def egc_forward(ix: EdgeIndex, x, y, G, P, n_w, n_b, e_w, e_b, *, norm_nodes: in
     new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
     x_out = None if norm_nodes == NORM_STATS else new(Nn, d)
     y_out = new(Ne, d) if (need_edge_out and norm_edges != NORM_STATS) else None
-    M = new(Ne, d) if save else None
+    if gate_is_m and norm_edges == NORM_STATS and need_edge_out:
+        raise RuntimeError("egc_forward(gate_is_m=True): finalize the batch statistics of m first and pass NORM_AFFINE")
+    M = (G if gate_is_m else new(Ne, d)) if save else None
     XP, S, H = (new(Nn, d), new(Nn, d), new(Nn, d)) if save else (None, None, None)
     partials = new(partial_rows(Nn, d), 4, d) if stats else None
     a = _lib.EgcFwdArgs(
         struct_size=C.sizeof(_lib.EgcFwdArgs), Nn=Nn, Ne=Ne, d=d, norm_nodes=norm_nodes, norm_edges=norm_edges,
-        residual=int(residual), gate_eps=gate_eps, ln_eps=ln_eps,
+        residual=int(residual), gate_is_m=int(gate_is_m), gate_eps=gate_eps, ln_eps=ln_eps,
         x=ptr(x), y=ptr(y), G=ptr(G), P=ptr(P), src=ptr(ix.src), in_ptr=ptr(ix.in_ptr),
         in_eid=None if ix.dst_sorted else ptr(ix.in_eid),
         n_w=ptr(n_w), n_b=ptr(n_b), e_w=ptr(e_w), e_b=ptr(e_b),
-        x_out=ptr(x_out), y_out=ptr(y_out), M=ptr(M), XP=ptr(XP), S=ptr(S), H=ptr(H), partials=ptr(partials),
+        x_out=ptr(x_out), y_out=ptr(y_out), M=None if gate_is_m else ptr(M), XP=ptr(XP), S=ptr(S), H=ptr(H),
+        partials=ptr(partials),
         stream=stream_ptr())
     span = None
     if TIMER is not None and Ne >= TIMER.min_edges:
         # compulsory bytes of THIS kernel: read G, P (each element once), indices; write what it writes
         nb = 4 * d * (Ne + 4 * Nn) + 4 * Ne + 4 * (Nn + 1)
-        nb += 4 * d * Ne * (M is not None) + 4 * d * Nn * 3 * (XP is not None)
+        nb += 4 * d * Ne * (M is not None and not gate_is_m) + 4 * d * Nn * 3 * (XP is not None)
         nb += 4 * d * Ne * (1 + int(residual)) * (y_out is not None) + 4 * d * Nn * (1 + int(residual)) * (x_out is not None)
-        span = TIMER.span("egc_forward_kernel", nb)
+        span = TIMER.span("egc_forward_kernel" + ("<gate_is_m>" if gate_is_m else ""), nb)
         span[0].record()
     _lib.check(lib.alignn_b200_egc_forward(C.byref(a)), "alignn_b200_egc_forward")
     if span is not None:
@@ -255,6 +262,56 @@ def gemm_nt(A: torch.Tensor, w: WeightImage, bias: Optional[torch.Tensor] = None
     _lib.check(lib.alignn_b200_gemm_nt(ptr_any(A), A.stride(0), ptr_any(w.buf), M, w.N, w.K, ptr_any(bias), ptr_any(residual),
                                         ldr, ptr_any(out), out.stride(0), stream_ptr()), "alignn_b200_gemm_nt")
     return out
+
+
+def gemm_gather(A: torch.Tensor, w: WeightImage, bias: Optional[torch.Tensor] = None, *,
+                add0: Optional[torch.Tensor] = None, idx0: Optional[torch.Tensor] = None,
+                add1: Optional[torch.Tensor] = None, idx1: Optional[torch.Tensor] = None,
+                stats: bool = False, out: Optional[torch.Tensor] = None):
+    """out[r] = A[r] @ W^T (+ bias) (+ add0[idx0[r]]) (+ add1[idx1[r]]) on tcgen05, A streamed by TMA tiles.
+
+    add0 / add1 are 2-D fp32 views with unit column stride and w.N columns (column slices of a wider matrix are fine);
+    idx None = identity (a residual).  stats=True also returns the per-CTA partial column sums [rows, 2, N] of out and
+    out^2 (alignn.py:123 batch statistics; feed `bn_finalize(partials, 0, M, ...)`)."""
+    lib = _lib.load()
+    if A.dim() != 2 or A.stride(1) != 1 or A.shape[1] != w.K:
+        raise RuntimeError(f"gemm_gather: A must be [M,{w.K}] with unit column stride, got {tuple(A.shape)}/{A.stride()}")
+    M = A.shape[0]
+    for t in (A, bias, add0, add1, out):
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+            raise RuntimeError("gemm_gather needs fp32 CUDA tensors")
+    for t, ix in ((add0, idx0), (add1, idx1)):
+        if t is None:
+            if ix is not None:
+                raise RuntimeError("gemm_gather: index without addend")
+            continue
+        if t.dim() != 2 or t.stride(1) != 1 or t.shape[1] != w.N:
+            raise RuntimeError("gemm_gather: addend must be [rows, N] with unit column stride")
+        if ix is None and t.shape[0] != M:
+            raise RuntimeError("gemm_gather: identity-indexed addend must have M rows")
+        if ix is not None and (ix.dtype != torch.int32 or not ix.is_cuda or not ix.is_contiguous() or ix.numel() != M):
+            raise RuntimeError("gemm_gather: index must be a contiguous int32 CUDA tensor with M entries")
+    if out is None:
+        out = torch.empty(M, w.N, device=A.device, dtype=torch.float32)
+    part = None
+    if stats:
+        rows = int(lib.alignn_b200_gemm_gather_stat_rows(M, w.N))
+        part = torch.empty(max(rows, 1), 2, w.N, device=A.device, dtype=torch.float32)
+    a = _lib.GemmGatherArgs(
+        struct_size=C.sizeof(_lib.GemmGatherArgs), M=M, N=w.N, K=w.K, A=ptr_any(A), lda=A.stride(0),
+        w_image=ptr_any(w.buf), bias=ptr_any(bias),
+        add0=ptr_any(add0), ld0=add0.stride(0) if add0 is not None else 0, idx0=ptr_any(idx0),
+        add1=ptr_any(add1), ld1=add1.stride(0) if add1 is not None else 0, idx1=ptr_any(idx1),
+        C=ptr_any(out), ldc=out.stride(0), stats=ptr_any(part), stream=stream_ptr())
+    span = None
+    if TIMER is not None and M >= TIMER.min_edges:
+        nb = 4 * M * (w.K + w.N) + (8 * M if idx0 is not None else 0) + (4 * M * w.N if (add0 is not None and idx0 is None) else 0)
+        span = TIMER.span(f"gemm_gather<{w.N}>" + ("+gather" if idx0 is not None else "") + ("+res" if (add0 is not None and idx0 is None) else ""), nb)
+        span[0].record()
+    _lib.check(lib.alignn_b200_gemm_gather(C.byref(a)), "alignn_b200_gemm_gather")
+    if span is not None:
+        span[1].record()
+    return (out, part) if stats else out
 
 
 def wgrad_supported(DA: int, DB: int) -> bool:

@@ -83,6 +83,9 @@ typedef struct {
   int32_t d;
   int32_t norm_nodes, norm_edges; /* alignn_b200_norm */
   int32_t residual;               /* alignn.py:125 */
+  int32_t gate_is_m;              /* != 0: G already holds m = e_src[src] + e_dst[dst] + edge_gate(y) (written with its
+                                     batch statistics by alignn_b200_gemm_gather): no e_src / e_dst gathers, M is not
+                                     written, no edge statistics; norm_edges must then be LAYER or AFFINE (or y_out NULL) */
   float gate_eps;                 /* 1e-6, alignn.py:109 */
   float ln_eps;                   /* LayerNorm eps */
   /* inputs */
@@ -214,6 +217,35 @@ int alignn_b200_gemm_prepare_weights(const float* W, int N, int K, int64_t ldw, 
                                      alignn_stream_t stream);
 int alignn_b200_gemm_nt(const float* A, int64_t lda, const void* w_image, int64_t M, int N, int K, const float* bias,
                         const float* R, int64_t ldr, float* C, int64_t ldc, alignn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Linear layer with a gather-add epilogue and optional column statistics (csrc/gemm_fused_tc.cu):
+ *     C[r, 0:N] = A[r, 0:K] * W^T (+ bias) (+ add0[i0(r), 0:N]) (+ add1[i1(r), 0:N]),   i(r) = idx ? idx[r] : r
+ *     stats[blk][0][c] / stats[blk][1][c] = per-CTA partial sums of C[:, c] and C[:, c]^2  (optional; needs N in
+ *     {32, 64, 128, 256}; rows = alignn_b200_gemm_gather_stat_rows(M, N); feed alignn_b200_bn_finalize, which = 0)
+ * The edge-gate use (alignn/models/alignn.py:98-101, 123): A = edge_feats, W = edge_gate.weight,
+ * add0 = P + 0 (ld 4d, idx0 = src: e_src), add1 = P + 2d (ld 4d, idx1 = dst: e_dst, bias of edge_gate folded into the
+ * dst_gate bias by the caller) gives m = e_src[src] + e_dst[dst] + edge_gate(y) and the batch statistics of
+ * BatchNorm1d(m) in one pass over y -- apply_edges(u_add_v) and the Linear fused, no [Ne,d] temporary.
+ * With add0 = R, idx0 = NULL it is the data-gradient GEMM with its residual; without addends a plain Linear.
+ * A is streamed by TMA tensor tiles (row stride lda floats, 16-byte aligned rows); W is an image from
+ * alignn_b200_gemm_prepare_weights.  Constraints: K % 32 == 0, N % 32 == 0, lda/ldc/ld0/ld1 % 4 == 0.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  size_t struct_size;
+  int64_t M; int32_t N, K;
+  const float* A; int64_t lda;
+  const void* w_image;
+  const float* bias;                                        /* [N] or NULL */
+  const float* add0; int64_t ld0; const int32_t* idx0;      /* addend rows (NULL: none); idx NULL = identity */
+  const float* add1; int64_t ld1; const int32_t* idx1;
+  float* C; int64_t ldc;
+  float* stats;                                             /* [stat_rows][2][N] or NULL */
+  alignn_stream_t stream;
+} alignn_b200_gemm_gather_args;
+
+int alignn_b200_gemm_gather(const alignn_b200_gemm_gather_args* args);
+int alignn_b200_gemm_gather_stat_rows(int64_t M, int N);
 
 /* Weight gradients on the tensor cores (split-K over the batch rows, deterministic two-stage sum):
  *     out[g*DA + o, i] = sum_{r < K} A[r, g*DA + o] * B[r, i]        g < groups,  o < DA,  i < DB

@@ -92,3 +92,56 @@ def test_wgrad_rectangular_matches_fp64(K, DA, DB):
     assert out.shape == (DA, DB)
     assert (out.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
     assert not ops.wgrad_supported(48, 64)
+
+
+# ---- gemm_gather: TMA-fed Linear with gather-add epilogue and column statistics (csrc/gemm_fused_tc.cu) -------------
+@pytest.mark.parametrize("M,N,K", [(1, 32, 32), (127, 64, 64), (128, 256, 256), (129, 128, 96), (1000, 256, 256),
+                                   (1920, 1024, 256), (23040, 256, 1024), (5000, 64, 96), (276480, 256, 256)])
+def test_gemm_gather_plain_matches_fp64_and_gemm_nt(M, N, K):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    img = ops.WeightImage(W)
+    for b in (None, bias):
+        out = ops.gemm_gather(A, img, b)
+        ref = _ref(A, W, b, None)
+        err = (out.double() - ref).abs().max().item()
+        assert err <= 2e-5 * ref.abs().max().item(), (M, N, K, err, ref.abs().max().item())
+        # same operand split, same MMA order, same epilogue association: bit-identical to the register-fed kernel
+        assert torch.equal(out, ops.gemm_nt(A, img, b))
+
+
+@pytest.mark.parametrize("M,Nn,d", [(5, 3, 32), (384, 32, 64), (1000, 77, 128), (23040, 1920, 256), (70001, 5000, 256)])
+def test_gemm_gather_edge_gate_matches_fp64(M, Nn, d):
+    """m = e_src[src] + e_dst[dst] + edge_gate(y) and its column sums (alignn.py:98-101, 123)."""
+    g = torch.Generator(device="cpu").manual_seed(M + Nn + d)
+    y = torch.randn(M, d, generator=g).to(DEV)
+    W = (torch.randn(d, d, generator=g) / d ** 0.5).to(DEV)
+    P = torch.randn(Nn, 4 * d, generator=g).to(DEV)
+    src = torch.randint(0, Nn, (M,), generator=g).to(torch.int32).to(DEV)
+    dst = torch.randint(0, Nn, (M,), generator=g).to(torch.int32).to(DEV)
+    img = ops.WeightImage(W)
+    out, part = ops.gemm_gather(y, img, None, add0=P[:, 0:d], idx0=src, add1=P[:, 2 * d:3 * d], idx1=dst, stats=True)
+    ref = y.double() @ W.double().t() + P[:, 0:d].double()[src.long()] + P[:, 2 * d:3 * d].double()[dst.long()]
+    scale = ref.abs().max().item()
+    assert (out.double() - ref).abs().max().item() <= 2e-5 * scale
+    s = part.double().sum(0)
+    assert (s[0] - ref.sum(0)).abs().max().item() <= 1e-5 * ref.abs().sum(0).max().item()
+    assert (s[1] - (ref * ref).sum(0)).abs().max().item() <= 1e-5 * (ref * ref).sum(0).max().item()
+    # deterministic
+    out2, part2 = ops.gemm_gather(y, img, None, add0=P[:, 0:d], idx0=src, add1=P[:, 2 * d:3 * d], idx1=dst, stats=True)
+    assert torch.equal(out, out2) and torch.equal(part, part2)
+
+
+def test_gemm_gather_residual_and_strided_views():
+    """Data-gradient form with the residual in the epilogue: gy = GM W + gy_out; A a column slice of a wider matrix."""
+    g = torch.Generator(device="cpu").manual_seed(11)
+    G = torch.randn(3000, 1024, generator=g).to(DEV)
+    W = (torch.randn(256, 256, generator=g) / 16).to(DEV)
+    R = torch.randn(3000, 256, generator=g).to(DEV)
+    img_t = ops.WeightImage(W, transpose=True)
+    A = G[:, 512:768]
+    out = ops.gemm_gather(A, img_t, None, add0=R)
+    ref = A.double() @ W.double() + R.double()
+    assert (out.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()

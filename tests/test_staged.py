@@ -247,7 +247,7 @@ def test_fused_conv_forward_matches_shipped_forward(staged, mode, groups):
                 for u, v in zip(a, b):
                     assert torch.allclose(u, v, rtol=1e-5, atol=1e-6)
         else:
-            tol = 0.0 if mode == "bn_eval" else 1e-5
+            tol = 1e-6 if mode == "bn_eval" else 1e-5   # the node tail is a separate kernel: FMA contraction may differ
             for k in ("x_out", "y_out"):
                 err = (out[k] - ref[k]).abs().max().item()
                 assert err <= tol * max(ref[k].abs().max().item(), 1.0), (mode, k, err)
@@ -288,7 +288,7 @@ def test_device_csr_and_line_graph_bit_identical_to_host_builders(staged):
 def test_device_force_scatter_and_virial_match_fp64(staged):
     import staged_binding
     from oracle import alignn_oracle as O
-    from helpers import to_oracle
+    from tests.helpers import to_oracle
     dev = torch.device("cuda:0")
     g, _, _, _ = synthetic.make_batch(batch_size=3, atoms=7, k=12, seed=37, vary_atoms=True)
     E = g.num_edges()
@@ -464,8 +464,12 @@ def test_fused_backward_matches_shipped_backward(staged, d, dead_edge_out):
         close(out["GM"], GM, "GM")
         close(out["GP"][:, 2 * d:3 * d], GP[:, 2 * d:3 * d], "GP e_dst")
         close(out["GP"][:, 3 * d:], GP[:, 3 * d:], "GP src_update")
-        close(out["sum_gD"], vd[4], "sum dL/dx'", 1e-4)
-        close(out["sum_gm"], vd[5], "sum gm", 1e-4)
+        # column sums of dL/dx' are mathematically zero in train-mode BatchNorm: judge them against the summands' scale
+        def close_sum(a_, b_, what, scale):
+            err = (a_ - b_).abs().max().item()
+            assert err <= 1e-4 * scale, (what, err, scale)
+        close_sum(out["sum_gD"], vd[4], "sum dL/dx'", GP[:, 3 * d:].abs().sum(0).max().item())
+        close_sum(out["sum_gm"], vd[5], "sum gm", GM.abs().sum(0).max().item())
         close(out["gy"], gy_ref, "gy", 1e-4)      # the fused GEMM consumes the same gm to within the rounding of gm itself
 
 

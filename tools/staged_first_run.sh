@@ -9,14 +9,14 @@ mkdir -p gpurun_out
 export ALIGNN_B200_STAGED=1
 python tools/build_staged.py > gpurun_out/staged_build.log 2>&1 || { echo "staged build failed"; tail -5 gpurun_out/staged_build.log; exit 1; }
 # 1. integer builders and the d=3 reductions first: simple kernels, independent of the tcgen05 one
-timeout 300 python -m pytest tests/test_staged.py -m gpu -x -q -k "device" > gpurun_out/staged_device_tests.log 2>&1
+timeout 300 python -m pytest tests/test_staged.py -m gpu -q -k "device" > gpurun_out/staged_device_tests.log 2>&1
 echo "device builders: exit $?"; tail -3 gpurun_out/staged_device_tests.log
 # 2. the fused forward, smallest configuration first
-timeout 300 python -m pytest tests/test_staged.py -m gpu -x -q -k "fused and not backward" > gpurun_out/staged_fused_tests.log 2>&1
+timeout 300 python -m pytest tests/test_staged.py -m gpu -q -k "fused and not backward" > gpurun_out/staged_fused_tests.log 2>&1
 rc=$?
 echo "fused forward: exit $rc"; tail -15 gpurun_out/staged_fused_tests.log
 # 2b. the fused backward (independent of the forward kernel's result)
-timeout 300 python -m pytest tests/test_staged.py -m gpu -x -q -k "fused_backward" > gpurun_out/staged_bwd_tests.log 2>&1
+timeout 300 python -m pytest tests/test_staged.py -m gpu -q -k "fused_backward" > gpurun_out/staged_bwd_tests.log 2>&1
 rcb=$?
 echo "fused backward: exit $rcb"; tail -15 gpurun_out/staged_bwd_tests.log
 if [ $rcb -eq 0 ]; then
