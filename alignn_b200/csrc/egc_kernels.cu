@@ -35,6 +35,7 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
   const bool train = a.XP != nullptr;      // (M is a null pointer for an edgeless graph, so XP marks training)
+  const bool want_res = a.residual && a.y_out && a.norm_edges != ALIGNN_NORM_STATS;
   const bool stats = a.partials != nullptr;
   {
     const float* srcs[4] = {a.n_w, a.n_b, a.e_w, a.e_b};
@@ -62,7 +63,8 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
         my_s = a.src[my_e];
       }
       // everything of one edge after its three rows have arrived
-      auto edge_tail = [&](int64_t e, float (&m)[V], const float (&cv)[V]) {
+      // yr: the edge's residual row (requested together with its other rows, not after the gate math) when used
+      auto edge_tail = [&](int64_t e, float (&m)[V], const float (&cv)[V], const float (&yr)[V]) {
 #pragma unroll
         for (int k = 0; k < V; ++k) {
           const float sg = sigmoidf_(m[k]);
@@ -89,8 +91,6 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
             for (int k = 0; k < V; ++k) o[k] = silu_(m[k] * ew[k] + eb[k]);
           }
           if (a.residual) {
-            float yr[V];
-            ld_row<D, true>(yr, a.y + e * D, lane);
 #pragma unroll
             for (int k = 0; k < V; ++k) o[k] += yr[k];
           }
@@ -101,9 +101,13 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
       for (; i + 1 < cnt; i += 2) {   // two edges (six row loads) in flight per warp
         const int64_t e0 = __shfl_sync(0xffffffffu, my_e, i), s0 = __shfl_sync(0xffffffffu, my_s, i);
         const int64_t e1 = __shfl_sync(0xffffffffu, my_e, i + 1), s1 = __shfl_sync(0xffffffffu, my_s, i + 1);
-        float g0[V], a0[V], c0[V], g1[V], a1[V], c1[V];
+        float g0[V], a0[V], c0[V], g1[V], a1[V], c1[V], y0[V], y1[V];
         ld_row<D, true>(g0, a.G + e0 * D, lane);
         ld_row<D, true>(g1, a.G + e1 * D, lane);
+        if (want_res) {
+          ld_row<D, true>(y0, a.y + e0 * D, lane);
+          ld_row<D, true>(y1, a.y + e1 * D, lane);
+        }
         if constexpr (!GIM) {
           ld_row<D, false>(a0, a.P + s0 * 4 * D, lane);
           ld_row<D, false>(a1, a.P + s1 * 4 * D, lane);
@@ -114,20 +118,21 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
 #pragma unroll
           for (int k = 0; k < V; ++k) { g0[k] += a0[k] + bv[k]; g1[k] += a1[k] + bv[k]; }
         }
-        edge_tail(e0, g0, c0);
-        edge_tail(e1, g1, c1);
+        edge_tail(e0, g0, c0, y0);
+        edge_tail(e1, g1, c1, y1);
       }
       if (i < cnt) {
         const int64_t e0 = __shfl_sync(0xffffffffu, my_e, i), s0 = __shfl_sync(0xffffffffu, my_s, i);
-        float g0[V], a0[V], c0[V];
+        float g0[V], a0[V], c0[V], y0[V];
         ld_row<D, true>(g0, a.G + e0 * D, lane);
+        if (want_res) ld_row<D, true>(y0, a.y + e0 * D, lane);
         if constexpr (!GIM) ld_row<D, false>(a0, a.P + s0 * 4 * D, lane);
         ld_row<D, false>(c0, a.P + s0 * 4 * D + D, lane);
         if constexpr (!GIM) {
 #pragma unroll
           for (int k = 0; k < V; ++k) g0[k] += a0[k] + bv[k];
         }
-        edge_tail(e0, g0, c0);
+        edge_tail(e0, g0, c0, y0);
       }
     }
     // ---- node finalize: h = Sh/(S+eps); x' = src_update(x) + h; norm; silu; residual -----------

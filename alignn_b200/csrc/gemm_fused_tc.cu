@@ -33,17 +33,20 @@ namespace gemm2 {
 
 constexpr int BM = 128;
 constexpr int BK = 32;
-constexpr int NSA = 4;          // fp32 A staging ring (TMA destination)
+constexpr int NSA = 3;          // fp32 A staging ring (TMA destination); L2 prefetch one tile ahead covers the HBM latency
 constexpr int NSP = 2;          // bf16 A plane ring
 constexpr int NSB = 3;          // W chunk ring
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;          // two per TMEM lane quarter, alternating 32-column chunks
 constexpr int CONV_WARPS = 4;
 constexpr int THREADS = 32 * (4 + EPI_WARPS + CONV_WARPS);   // 384
 constexpr uint32_t LBO = 128;
 constexpr uint32_t SBO = (BK / 8) * 128;
 constexpr int A_STAGE = BM * BK * 4;          // 16 KB fp32 box
 constexpr int A_PLANE = BM * BK * 2;          // 8 KB bf16 plane
-constexpr int EPI_STRIDE = 36;                // floats per staged row (32 + 4 pad: conflict-free both ways)
+constexpr int EPI_BOX = 32 * 32 * 4;          // one warp's [32 rows x 32 floats] transpose box (128-byte swizzle)
+constexpr bool kTmaStore = true;              // true: finished boxes leave by TMA tile stores (costs 2 more passes over shared
+                                              // memory per tile; the kernel is bound by shared-memory bandwidth)
+constexpr int EPI_BUFS = 1;
 
 template <int BN>
 struct Cfg {
@@ -51,10 +54,10 @@ struct Cfg {
   static constexpr int OFF_ASTG = 0;                                   // 1024-byte aligned boxes
   static constexpr int OFF_APL = OFF_ASTG + NSA * A_STAGE;
   static constexpr int OFF_B = OFF_APL + NSP * 2 * A_PLANE;
-  static constexpr int OFF_EPI = OFF_B + NSB * 2 * B_PLANE;
-  static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_STRIDE * 4;
+  static constexpr int OFF_EPI = (OFF_B + NSB * 2 * B_PLANE + 1023) / 1024 * 1024;
+  static constexpr int EPI_BYTES = EPI_WARPS * EPI_BUFS * EPI_BOX;
   static constexpr int OFF_STAT = OFF_EPI + EPI_BYTES;                 // [EPI_WARPS][2][BN] floats
-  static constexpr int STAT_BYTES = EPI_WARPS * 2 * BN * 4;
+  static constexpr int STAT_BYTES = 4 * 2 * BN * 4;                    // per lane quarter (its two warps own disjoint columns)
   static constexpr int OFF_BAR = OFF_STAT + STAT_BYTES;
   static constexpr int SMEM = OFF_BAR + 256;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
@@ -81,13 +84,17 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
   asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(tc::smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(tc::smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(tc::smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const Params p) {
+gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapC, const Params p) {
   using F = Cfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* astg_full = reinterpret_cast<uint64_t*>(smem + F::OFF_BAR);
@@ -185,8 +192,6 @@ gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const Params
       float4 v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(src + ld_off[i]);
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&astg_empty[sa]);          // values are in registers: the box may be refilled
       if (c >= NSP) tc::mbar_wait(&apl_empty[sp], ((c / NSP) - 1) & 1);
       uint8_t* dst = smem + F::OFF_APL + sp * 2 * A_PLANE;
 #pragma unroll
@@ -198,18 +203,29 @@ gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const Params
       }
       tc::fence_async_smem();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&apl_full[sp]);
+      if (lane == 0) {
+        tc::mbar_arrive(&apl_full[sp]);
+        // the staged box is released only now: the plane stores above consumed every loaded value.  (Releasing right
+        // after issuing the shared-memory loads let the TMA refill overtake loads still queued in the LSU: stale
+        // 8-row groups, seen on hardware.)
+        tc::mbar_arrive(&astg_empty[sa]);
+      }
       if (cw == 0 && lane == 0) GEMM2_TRACE(3, tr3);
     }
   } else if (warp >= 4) {
     // ================= epilogue =================
     const int ew = warp - 4;
     const int q = warp & 3;                                  // TMEM lane quarter = rows 32q .. 32q+31 of the tile
-    float* stg = reinterpret_cast<float*>(smem + F::OFF_EPI) + ew * 32 * EPI_STRIDE;
-    float* stat = reinterpret_cast<float*>(smem + F::OFF_STAT) + ew * 2 * BN;
+    uint8_t* stg0 = smem + F::OFF_EPI + ew * EPI_BUFS * EPI_BOX;
+    // staged element (row r, 16-byte chunk j) lives at r * 128 + ((j ^ (r & 7)) << 4): what a SWIZZLE_128B tensor map
+    // expects, and conflict-free for both the row-per-thread writes and the 8-lanes-per-row reads
+    const int st_row = lane * 128, st_sw = lane & 7;
+    uint32_t chunk_ctr = 0;
+    float* stat = reinterpret_cast<float*>(smem + F::OFF_STAT) + q * 2 * BN;
+    const int half = ew >> 2;                                // which of the quarter's two warps: chunks half, half + 2, ...
     const bool do_stats = p.stats != nullptr;
     if (do_stats)
-      for (int i = lane; i < 2 * BN; i += 32) stat[i] = 0.f;
+      for (int ch = half; ch < BN / 32; ch += 2) { stat[ch * 32 + lane] = 0.f; stat[BN + ch * 32 + lane] = 0.f; }
     const int rsub = lane >> 3;                              // row within a group of 4
     const int c4 = (lane & 7) * 4;                           // 4 of the chunk's 32 columns
     constexpr int NCH = BN / 32;
@@ -229,50 +245,72 @@ gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const Params
         i0[it] = (p.add0 && ok) ? (p.idx0 ? __ldg(p.idx0 + gr) : gr) : -1;
         i1[it] = (p.add1 && ok) ? (p.idx1 ? __ldg(p.idx1 + gr) : gr) : -1;
       }
-      const float* base0 = p.add0 + n0 + c4;
-      const float* base1 = p.add1 + n0 + c4;
+      const float* base0 = p.add0 + n0 + c4 + half * 32;       // first chunk of this warp
+      const float* base1 = p.add1 + n0 + c4 + half * 32;
       float4 a0[8], a1[8];
       const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
-        a0[it] = i0[it] >= 0 ? __ldg(reinterpret_cast<const float4*>(base0 + (int64_t)i0[it] * p.ld0)) : z4;
-        a1[it] = i1[it] >= 0 ? __ldg(reinterpret_cast<const float4*>(base1 + (int64_t)i1[it] * p.ld1)) : z4;
+        a0[it] = (i0[it] >= 0 && half < NCH) ? __ldg(reinterpret_cast<const float4*>(base0 + (int64_t)i0[it] * p.ld0)) : z4;
+        a1[it] = (i1[it] >= 0 && half < NCH) ? __ldg(reinterpret_cast<const float4*>(base1 + (int64_t)i1[it] * p.ld1)) : z4;
       }
       tc::mbar_wait(&tfull[acc], (lt >> 1) & 1);
       tc::fence_after_sync();
       if (ew == 0 && lane == 0) GEMM2_TRACE(5, tr5);
 #pragma unroll 1
-      for (int ch = 0; ch < NCH; ++ch) {
+      for (int ch = half; ch < NCH; ch += 2) {
         const int c0 = ch * 32;
+        uint8_t* stg = stg0;
+        if (kTmaStore && chunk_ctr >= 1) {       // the TMA store that read this box must be done with it
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
+        ++chunk_ctr;
         {
           float v[32];
           tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+          if (ew == 0 && lane == 0) GEMM2_TRACE(5, tr5);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(stg + lane * EPI_STRIDE + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stg + st_row + ((j ^ st_sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         __syncwarp();
+        if (ew == 0 && lane == 0) GEMM2_TRACE(5, tr5);
         float4 b4 = z4;
         if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + c4));
         float4 s4 = z4, q4 = z4;
-        const bool more = ch + 1 < NCH;
+        const bool more = ch + 2 < NCH;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          float4 o = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * EPI_STRIDE + c4);
+          const int r = it * 4 + rsub;
+          float4* cell = reinterpret_cast<float4*>(stg + r * 128 + (((lane & 7) ^ (r & 7)) << 4));
+          float4 o = *cell;
           o.x = (o.x + b4.x) + (a0[it].x + a1[it].x);
           o.y = (o.y + b4.y) + (a0[it].y + a1[it].y);
           o.z = (o.z + b4.z) + (a0[it].z + a1[it].z);
           o.w = (o.w + b4.w) + (a0[it].w + a1[it].w);
           // this row's addends of the NEXT chunk go out now and land while the rest of this chunk is processed
           if (more) {
-            if (i0[it] >= 0) a0[it] = __ldg(reinterpret_cast<const float4*>(base0 + (int64_t)i0[it] * p.ld0 + c0 + 32));
-            if (i1[it] >= 0) a1[it] = __ldg(reinterpret_cast<const float4*>(base1 + (int64_t)i1[it] * p.ld1 + c0 + 32));
+            if (i0[it] >= 0) a0[it] = __ldg(reinterpret_cast<const float4*>(base0 + (int64_t)i0[it] * p.ld0 + (c0 - half * 32) + 64));
+            if (i1[it] >= 0) a1[it] = __ldg(reinterpret_cast<const float4*>(base1 + (int64_t)i1[it] * p.ld1 + (c0 - half * 32) + 64));
           }
           if ((rvm >> it) & 1u) {
-            *reinterpret_cast<float4*>(p.C + (int64_t)(m0 + q * 32 + it * 4 + rsub) * p.ldc + n0 + c0 + c4) = o;
             s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
             q4.x = fmaf(o.x, o.x, q4.x); q4.y = fmaf(o.y, o.y, q4.y); q4.z = fmaf(o.z, o.z, q4.z); q4.w = fmaf(o.w, o.w, q4.w);
           }
+          if constexpr (kTmaStore) *cell = o;
+          else if ((rvm >> it) & 1u)
+            *reinterpret_cast<float4*>(p.C + (int64_t)(m0 + q * 32 + r) * p.ldc + n0 + c0 + c4) = o;
+        }
+        if constexpr (kTmaStore) {   // finished [32 x 32] box -> global by TMA (rows past M are clipped by the tensor map)
+          tc::fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&mapC, stg, n0 + c0, m0 + q * 32);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else {
+          __syncwarp();               // the transpose box is rewritten by the next chunk
         }
         if (do_stats) {
           // lanes with equal (lane & 7) hold the same columns for different rows: fold them, fixed order
@@ -297,6 +335,7 @@ gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const Params
       if (lane == 0) tc::mbar_arrive(&tempty[acc]);
       if (ew == 0 && lane == 0) GEMM2_TRACE(5, tr5);
     }
+    if (kTmaStore && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // smem must outlive the last TMA stores
     if (do_stats) {
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       const float* all = reinterpret_cast<const float*>(smem + F::OFF_STAT);
@@ -304,7 +343,7 @@ gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const Params
       for (int i = ew * 32 + lane; i < 2 * BN; i += EPI_WARPS * 32) {
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < EPI_WARPS; ++w) t += all[w * 2 * BN + i];
+        for (int w = 0; w < 4; ++w) t += all[w * 2 * BN + i];
         out_row[i] = t;
       }
     }
@@ -386,7 +425,7 @@ static long long* g_trace = nullptr;   // set by alignn_b200_debug_gemm_trace (d
 inline int pick_bn(int N) { return (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : (N % 32 == 0) ? 32 : 0; }
 
 template <int BN>
-int launch(const CUtensorMap& mapA, const Params& p, cudaStream_t st) {
+int launch(const CUtensorMap& mapA, const CUtensorMap& mapC, const Params& p, cudaStream_t st) {
   using F = Cfg<BN>;
   static std::atomic<bool> configured{false};
   if (!configured.load(std::memory_order_acquire)) {
@@ -396,7 +435,7 @@ int launch(const CUtensorMap& mapA, const Params& p, cudaStream_t st) {
   }
   const int total = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = total < 148 ? total : 148;
-  gemm_gather_bf16x3_kernel<BN><<<grid, THREADS, F::SMEM, st>>>(mapA, p);
+  gemm_gather_bf16x3_kernel<BN><<<grid, THREADS, F::SMEM, st>>>(mapA, mapC, p);
   return check_launch();
 }
 
@@ -428,8 +467,10 @@ int alignn_b200_gemm_gather(const alignn_b200_gemm_gather_args* a) {
   const int bn = pick_bn(a->N);
   if (bn == 0) return ALIGNN_ERR_UNSUPPORTED_D;
   if (a->stats && a->N != bn) return ALIGNN_ERR_BAD_ARG;      // column statistics need the whole row in one tile
-  CUtensorMap mapA;
+  CUtensorMap mapA, mapC;
   int rc = make_map_f32(&mapA, a->A, a->M, a->K, a->lda, BM);
+  if (rc != ALIGNN_OK) return rc;
+  rc = make_map_f32(&mapC, a->C, a->M, a->N, a->ldc, 32);
   if (rc != ALIGNN_OK) return rc;
   Params p;
   p.M = (int)a->M; p.N = a->N; p.K = a->K;
@@ -441,10 +482,10 @@ int alignn_b200_gemm_gather(const alignn_b200_gemm_gather_args* a) {
   p.trace = g_trace;
   cudaStream_t st = (cudaStream_t)a->stream;
   switch (bn) {
-    case 256: return launch<256>(mapA, p, st);
-    case 128: return launch<128>(mapA, p, st);
-    case 64: return launch<64>(mapA, p, st);
-    default: return launch<32>(mapA, p, st);
+    case 256: return launch<256>(mapA, mapC, p, st);
+    case 128: return launch<128>(mapA, mapC, p, st);
+    case 64: return launch<64>(mapA, mapC, p, st);
+    default: return launch<32>(mapA, mapC, p, st);
   }
 }
 

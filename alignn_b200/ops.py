@@ -401,11 +401,9 @@ class _MLPBNTrainFn(torch.autograd.Function):
             w = torch.nn.functional.pad(weight, (0, k_pad - weight.shape[1]))
         else:
             w = weight.contiguous()
-        R = gemm_nt(x, WeightImage(w), bias.contiguous())
+        # Linear + per-channel batch statistics in one pass (column sums leave through the GEMM epilogue)
+        R, part = gemm_gather(x, WeightImage(w), bias.contiguous(), stats=True)
         n, d = R.shape
-        rows = partial_rows(n, d)
-        part = torch.empty(rows, 2, d, device=R.device, dtype=torch.float32)
-        _lib.check(lib.alignn_b200_rowstats_partials(ptr(R), n, d, ptr(part), rows, stream_ptr()), "alignn_b200_rowstats_partials")
         track = bn.track_running_stats and bn.running_mean is not None
         scale, shift, mean, rstd = bn_finalize(part, 0, n, gamma.contiguous(), beta.contiguous(), bn.eps, float(bn.momentum),
                                                bn.running_mean if track else None, bn.running_var if track else None)

@@ -54,4 +54,12 @@ m = [int(v) - t0 for v in t[4].tolist() if v > 0]
 per_tile = [m[i + 8] - m[i] for i in range(0, len(m) - 8, 8)]
 print("cycles per tile (MMA issue to MMA issue):", per_tile[:16])
 e = [int(v) - t0 for v in t[5].tolist() if v > 0]
-print("epilogue busy per tile:", [e[i + 1] - e[i] for i in range(0, len(e) - 1, 2)][:16])
+# per tile: ready, then per chunk (after tcgen05.ld, after staging), then released = 2 + 16 stamps
+NC = 4
+per = 2 + 2 * NC
+for ti in range(3):
+    seg = e[ti * per:(ti + 1) * per]
+    if len(seg) == per:
+        print(f"tile {ti}: ready {seg[0]}; per chunk (ld wait, staging, rest):",
+              [(seg[1 + 2 * c] - (seg[2 * c] if c else seg[0]), seg[2 + 2 * c] - seg[1 + 2 * c],
+                (seg[3 + 2 * c] if c < NC - 1 else seg[per - 1]) - seg[2 + 2 * c]) for c in range(NC)])
