@@ -70,6 +70,15 @@ class GemmGatherArgs(C.Structure):
     ]
 
 
+class ImageEntry(C.Structure):
+    _fields_ = [("W", _fp), ("ldw", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32), ("transpose", C.c_int32),
+                ("n_off", C.c_int32), ("k_off", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("image", _fp)]
+
+
+class BiasEntry(C.Structure):
+    _fields_ = [("a", _fp), ("b", _fp), ("dst", _fp), ("n", C.c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/alignn_b200.h one to one
 _SIGNATURES = {
     "alignn_b200_version": (C.c_int, []),
@@ -90,6 +99,7 @@ _SIGNATURES = {
     "alignn_b200_gather_segment_sum": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int64, C.c_int, _fp, _fp, _fp]),
     "alignn_b200_gemm_weight_image_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "alignn_b200_gemm_prepare_weights": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int64, C.c_int, _fp, _fp]),
+    "alignn_b200_gemm_prepare_table": (C.c_int, [_fp, C.c_int, C.c_int64, _fp, C.c_int, _fp]),
     "alignn_b200_gemm_nt": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, C.c_int, C.c_int, _fp, _fp, C.c_int64, _fp,
                                       C.c_int64, _fp]),
     "alignn_b200_gemm_gather": (C.c_int, [C.POINTER(GemmGatherArgs)]),

@@ -19,7 +19,7 @@ from pydantic_settings import BaseSettings, SettingsConfigDict
 from torch import nn
 
 from . import ops
-from .conv import ALIGNNConvBase, EdgeGatedGraphConvBase
+from .conv import ALIGNNConvBase, EdgeGatedGraphConvBase, second_order
 from .graph import as_graph
 
 
@@ -72,11 +72,13 @@ def mlp_forward(layer: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
     the tcgen05 bf16x3 kernels when its shape is one the library supports (the angle/bond embeddings act on
     T = 276 480 rows per batch); norm and SiLU stay plain library layers."""
     lin, norm = layer[0], layer[1]
+    if second_order.active:                 # force / stress training: everything must be differentiable twice
+        return layer(x)
     if x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and ops.tc_linear_supported(lin.in_features, lin.out_features):
         if (isinstance(norm, nn.BatchNorm1d) and norm.training and norm.momentum is not None and norm.affine
                 and torch.is_grad_enabled()):
             return ops.mlp_bn_train(x, lin, norm)        # Linear + batch statistics + normalise + SiLU on library kernels
-        h = ops.tc_linear(x, lin.weight, lin.bias)
+        h = ops.tc_linear(x, lin)
     else:
         h = lin(x)
     return layer[2](norm(h))
@@ -164,8 +166,27 @@ class ALIGNN(nn.Module):
             x, y = layer(g, x, y, _need_edge_out=(i + 1 < n_gcn))
         return x, y
 
+    def refresh_images(self):
+        """One table-driven launch rebuilds the bf16 operand images of every conv and embedding Linear whose weight
+        changed since the last call (training: once per step; inference: once)."""
+        dev = self.fc.weight.device
+        if dev.type != "cuda":
+            return
+        tbl = getattr(self, "_alignn_b200_images", None)
+        if tbl is None or tbl.device != dev:
+            tbl = ops.ImageTable(dev)
+            for m in self.modules():
+                if isinstance(m, EdgeGatedGraphConvBase):
+                    tbl.absorb(m.image_table())
+                elif isinstance(m, nn.Sequential) and len(m) == 3 and isinstance(m[0], nn.Linear) and \
+                        ops.tc_linear_supported(m[0].in_features, m[0].out_features):
+                    tbl.absorb(ops.linear_table(m[0]))
+            object.__setattr__(self, "_alignn_b200_images", tbl)
+        tbl.refresh()
+
     def forward(self, g):
         """`g` is the 3-sequence (g, lg, lat) of alignn.py:294 (lat unused, as in the reference)."""
+        self.refresh_images()
         z = lg = None
         if len(self.alignn_layers) > 0:
             g, lg, _lat = g

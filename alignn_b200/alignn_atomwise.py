@@ -7,7 +7,7 @@ from __future__ import annotations
 
 from torch import nn
 
-from .conv import ALIGNNConvBase, EdgeGatedGraphConvBase
+from .conv import ALIGNNConvBase, EdgeGatedGraphConvBase, second_order
 
 
 class MLPLayer(nn.Module):
@@ -136,6 +136,8 @@ class ALIGNNAtomWise(nn.Module):
     def __init__(self, config: ALIGNNAtomWiseConfig = ALIGNNAtomWiseConfig(name="alignn_atomwise")):
         super().__init__()
         c = self.config = config
+        if c.gradwise_weight == 0:                 # alignn_atomwise.py:267-268: property-only models skip the force pass
+            c.calculate_gradient = False
         for flag, why in ((c.include_pos_deriv, "include_pos_deriv"),
                           (c.stresswise_weight != 0 and not c.batch_stress, "stresswise_weight != 0 with batch_stress=False"),
                           (c.stresswise_weight != 0 and not c.calculate_gradient, "stress without calculate_gradient"),
@@ -165,6 +167,18 @@ class ALIGNNAtomWise(nn.Module):
             self.fc.bias.data = torch.tensor(np.log(0.7), dtype=torch.float)
 
     def forward(self, g):
+        c = self.config
+        # Force / stress TRAINING differentiates through the force computation (create_graph=True, :530-539): the convs
+        # then run as differentiable torch-operator compositions (conv.second_order); inference, MD and property-only
+        # training use the once-differentiable CUDA kernels.
+        second = bool(self.training and torch.is_grad_enabled() and c.calculate_gradient
+                      and (c.gradwise_weight != 0 or c.stresswise_weight != 0))
+        if second:
+            with second_order():
+                return self._forward(g, True)
+        return self._forward(g, False)
+
+    def _forward(self, g, second: bool):
         c = self.config
         if len(self.alignn_layers) > 0:
             if len(g) != 3:
@@ -200,7 +214,7 @@ class ALIGNNAtomWise(nn.Module):
             x, y, z = layer(g, lg, x, y, z, _need_z_out=(i + 1 < n_al))
         for i, layer in enumerate(self.gcn_layers):
             x, y = layer(g, x, y, _need_edge_out=(i + 1 < n_gcn))
-        hpool = ops.segment_mean(x, g.node_graph_offsets())
+        hpool = ops.segment_mean_any_order(x, g.node_graph_offsets(), second)
         out = torch.squeeze(self.fc(hpool))
         additional = torch.empty(1)
         if c.additional_output_features > 0:
@@ -222,7 +236,7 @@ class ALIGNNAtomWise(nn.Module):
                 out = en_out
         if c.calculate_gradient:
             (dr,) = torch.autograd.grad(en_out, r, grad_outputs=torch.ones_like(en_out),
-                                        create_graph=False, retain_graph=self.training)
+                                        create_graph=second, retain_graph=second or self.training)
             pair_forces = c.grad_multiplier * dr                         # (:530-539)
             if c.force_mult_natoms:
                 pair_forces = pair_forces * g.num_nodes()
@@ -234,7 +248,7 @@ class ALIGNNAtomWise(nn.Module):
             forces = torch.squeeze(forces)
             result["pair_forces"] = pair_forces
             if c.stresswise_weight != 0:
-                stress = virial_stress(r.detach(), pair_forces, g.node_graph_offsets(), g.batch_num_edges(),
+                stress = virial_stress(r if second else r.detach(), pair_forces, g.node_graph_offsets(), g.batch_num_edges(),
                                        g.ndata["V"], c.stress_multiplier)
         if c.link == "log":
             out = torch.exp(out)

@@ -32,16 +32,53 @@ GATE_EPS = 1e-6   # alignn.py:109
 USE_GATHER_GEMM = os.environ.get("ALIGNN_B200_GATHER_GEMM", "1") != "0"
 
 
+class second_order:
+    """Context manager: run the convs as a composition of differentiable torch operators (ATen kernels on the same
+    device) instead of the once-differentiable CUDA Function.  Needed only where the reference differentiates through
+    its own backward -- force / stress training, `torch.autograd.grad(..., create_graph=True)` at
+    alignn/models/alignn_atomwise.py:530-539 (SURVEY.md section 8b "autograd contract").  Slower: every
+    intermediate is materialised, as in the reference."""
+    active = False
+
+    def __enter__(self):
+        self._prev = second_order.active
+        second_order.active = True
+
+    def __exit__(self, *exc):
+        second_order.active = self._prev
+
+
+def _torch_ops_forward(mod, ix, x, y, need_edge_out: bool):
+    """alignn/models/alignn.py:98-127 with plain torch operators (same summation structure as the reference's DGL
+    path: gather, multiply, index_add); differentiable to any order."""
+    F = torch.nn.functional
+    src, dst = ix.src.long(), ix.dst.long()
+    e_src, e_dst = mod.src_gate(x), mod.dst_gate(x)
+    m = e_src[src] + e_dst[dst] + mod.edge_gate(y)
+    sigma = torch.sigmoid(m)
+    Bh = mod.dst_update(x)
+    zeros = torch.zeros_like(Bh)
+    sum_sigma_h = zeros.index_add(0, dst, Bh[src] * sigma)
+    sum_sigma = zeros.index_add(0, dst, sigma)
+    h = sum_sigma_h / (sum_sigma + GATE_EPS)
+    xn = F.silu(mod.bn_nodes(mod.src_update(x) + h))
+    x_out = x + xn if mod.residual else xn
+    y_out = None
+    if need_edge_out or isinstance(mod.bn_edges, nn.BatchNorm1d):
+        yn = F.silu(mod.bn_edges(m))            # (BatchNorm: evaluated even when dead, for the running statistics)
+        y_out = (y + yn if mod.residual else yn) if need_edge_out else None
+    return x_out, y_out
+
+
 class _Cfg:
     """Per-call, non-tensor configuration of the fused stage."""
     __slots__ = ("index", "norm_nodes", "norm_edges", "residual", "need_edge_out", "ln_eps",
-                 "bn_nodes", "bn_edges", "n_aux", "e_aux")
+                 "bn_nodes", "bn_edges", "n_aux", "e_aux", "images", "legacy_w")
 
 
 def _bn_eval_vectors(bn: nn.BatchNorm1d):
     """scale/shift/mean/rstd of an eval-mode BatchNorm1d, cached on the module by tensor versions."""
-    key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
-           bn.weight.device)
+    key = tuple((t._version, t.data_ptr()) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var))
     cache = getattr(bn, "_alignn_b200_eval", None)
     if cache is not None and cache[0] == key:
         return cache[1]
@@ -80,15 +117,14 @@ class _EdgeGatedConvFn(torch.autograd.Function):
 
         # node projections P = [e_src | Bh | e_dst | src_update] (include/alignn_b200.h); the edge-gate bias rides in
         # the e_dst block, so the gate needs no bias of its own (weights are re-split every call: they change every step)
-        Wcat = torch.cat([W_sg, W_du, W_dg, W_su], 0)
         if USE_GATHER_GEMM:
-            bcat = torch.cat([b_sg, b_du, b_dg + b_eg, b_su], 0)
-            P = ops.gemm_gather(x, ops.WeightImage(Wcat), bcat)
+            img = cfg.images            # operand images, refreshed by one table-driven launch per step (ops.ImageTable)
+            P = ops.gemm_gather(x, img.images["cat"], img.vectors["bcat"])
             # pass 1 over the edge rows (csrc/gemm_fused_tc.cu): m = e_src[src] + e_dst[dst] + edge_gate(y) on tcgen05,
             # y streamed by TMA, the P rows gathered in the epilogue, BatchNorm batch statistics of m on the way out
             e_part = None
             if Ne > 0:
-                res = ops.gemm_gather(y, ops.WeightImage(W_eg.contiguous()), None, add0=P[:, 0:d], idx0=ix.src,
+                res = ops.gemm_gather(y, img.images["eg"], None, add0=P[:, 0:d], idx0=ix.src,
                                       add1=P[:, 2 * d:3 * d], idx1=ix.dst, stats=stats)
                 M, e_part = res if stats else (res, None)
             else:
@@ -114,6 +150,7 @@ class _EdgeGatedConvFn(torch.autograd.Function):
                                         bnn.running_mean if track_n else None, bnn.running_var if track_n else None)
                 x_out = ops.affine_silu_residual(out["XP"], x if cfg.residual else None, n_aux[0], n_aux[1])
         else:
+            Wcat = torch.cat([W_sg, W_du, W_dg, W_su], 0)
             bcat = torch.cat([b_sg, b_du, b_dg, b_su], 0)
             P = ops.gemm_nt(x, ops.WeightImage(Wcat), bcat)
             G = ops.gemm_nt(y, ops.WeightImage(W_eg.contiguous()), b_eg.contiguous())
@@ -140,7 +177,10 @@ class _EdgeGatedConvFn(torch.autograd.Function):
         if needs_grad:
             ctx.cfg = cfg
             cfg.n_aux, cfg.e_aux = n_aux, e_aux
-            ctx.save_for_backward(x, y, P, out["M"], out["XP"], out["S"], out["H"], Wcat, W_eg, nw, nb, ew, eb)
+            if not USE_GATHER_GEMM:
+                cfg.images = None
+                cfg.legacy_w = (Wcat, W_eg)
+            ctx.save_for_backward(x, y, P, out["M"], out["XP"], out["S"], out["H"], nw, nb, ew, eb)
         ctx.y_dead = y_out is None
         if y_out is None:       # dead edge output (or an edgeless graph): hand autograd an empty placeholder
             y_out = x.new_empty((0, d))
@@ -151,7 +191,12 @@ class _EdgeGatedConvFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, gx_out, gy_out):
         cfg = ctx.cfg
-        x, y, P, M, XP, S, H, Wcat, W_eg, nw, nb, ew, eb = ctx.saved_tensors
+        x, y, P, M, XP, S, H, nw, nb, ew, eb = ctx.saved_tensors
+        if cfg.images is not None:
+            img_catT, img_egT = cfg.images.images["catT"], cfg.images.images["egT"]
+        else:
+            img_catT = ops.WeightImage(cfg.legacy_w[0], transpose=True)
+            img_egT = ops.WeightImage(cfg.legacy_w[1].contiguous(), transpose=True)
         d = x.shape[1]
         gx_out = gx_out.contiguous()
         gy_out = None if (ctx.y_dead or gy_out is None) else gy_out.contiguous()
@@ -177,10 +222,9 @@ class _EdgeGatedConvFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         gx = gy = None
         if need[1]:
-            gx = ops.gemm_nt(GP, ops.WeightImage(Wcat, transpose=True), None, gx_out if cfg.residual else None)
+            gx = ops.gemm_gather(GP, img_catT, None, add0=gx_out if cfg.residual else None)
         if need[2]:
-            gy = ops.gemm_nt(GM, ops.WeightImage(W_eg.contiguous(), transpose=True), None,
-                             gy_out if (gy_out is not None and cfg.residual) else None)
+            gy = ops.gemm_gather(GM, img_egT, None, add0=gy_out if (gy_out is not None and cfg.residual) else None)
         gWcat = ops.wgrad(GP, x, groups=4)      # [4d, d] rows: src_gate | dst_update | dst_gate | src_update
         gW_eg = ops.wgrad(GM, y, groups=1)
         gW_sg, gW_du, gW_dg, gW_su = gWcat[0:d], gWcat[d:2 * d], gWcat[2 * d:3 * d], gWcat[3 * d:4 * d]
@@ -223,6 +267,27 @@ class EdgeGatedGraphConvBase(nn.Module):
         self.dst_update = nn.Linear(input_features, output_features)
         self.bn_nodes = mk()
 
+    def image_table(self) -> "ops.ImageTable":
+        """Operand images of the five Linear layers: node projections stacked [src_gate; dst_update; dst_gate;
+        src_update] (P column order of include/alignn_b200.h), their transposes for the data gradient, the edge gate and
+        its transpose, and the stacked bias with the edge-gate bias folded into the dst_gate block."""
+        dev = self.src_gate.weight.device
+        tbl = getattr(self, "_alignn_b200_images", None)
+        if tbl is not None and tbl.device == dev:
+            return tbl
+        d = self.src_gate.out_features
+        order = (self.src_gate, self.dst_update, self.dst_gate, self.src_update)
+        tbl = ops.ImageTable()
+        tbl.device = dev
+        tbl.add_image("cat", 4 * d, d, [(m.weight, False, i * d, 0) for i, m in enumerate(order)], dev)
+        tbl.add_image("catT", d, 4 * d, [(m.weight, True, 0, i * d) for i, m in enumerate(order)], dev)
+        tbl.add_image("eg", d, d, [(self.edge_gate.weight, False, 0, 0)], dev)
+        tbl.add_image("egT", d, d, [(self.edge_gate.weight, True, 0, 0)], dev)
+        tbl.add_vector("bcat", 4 * d, [(0, self.src_gate.bias, None), (d, self.dst_update.bias, None),
+                                       (2 * d, self.dst_gate.bias, self.edge_gate.bias), (3 * d, self.src_update.bias, None)], dev)
+        object.__setattr__(self, "_alignn_b200_images", tbl)
+        return tbl
+
     def forward(self, g, node_feats: torch.Tensor, edge_feats: torch.Tensor, _need_edge_out: bool = True):
         g = as_graph(g)
         if node_feats.dtype != torch.float32 or edge_feats.dtype != torch.float32:
@@ -237,12 +302,19 @@ class EdgeGatedGraphConvBase(nn.Module):
             raise RuntimeError("feature rows do not match the graph: "
                                f"{tuple(node_feats.shape)} nodes vs {g.num_nodes()}, "
                                f"{tuple(edge_feats.shape)} edges vs {g.num_edges()}")
+        if second_order.active:
+            return _torch_ops_forward(self, g.index, node_feats, edge_feats, _need_edge_out)
         cfg = _Cfg()
         cfg.index = g.index
         cfg.residual = bool(self.residual)
         cfg.need_edge_out = bool(_need_edge_out)
         cfg.bn_nodes, cfg.bn_edges = self.bn_nodes, self.bn_edges
         cfg.n_aux = cfg.e_aux = None
+        cfg.legacy_w = None
+        cfg.images = None
+        if USE_GATHER_GEMM:
+            cfg.images = self.image_table()
+            cfg.images.refresh()          # no launch if the model-level table already refreshed this step
         if self.norm_kind == "layernorm":
             cfg.norm_nodes = cfg.norm_edges = NORM_LAYER
             cfg.ln_eps = float(self.bn_nodes.eps)
@@ -250,13 +322,17 @@ class EdgeGatedGraphConvBase(nn.Module):
             use_batch_stats = self.training or not self.bn_nodes.track_running_stats
             cfg.norm_nodes = cfg.norm_edges = NORM_STATS if use_batch_stats else NORM_AFFINE
             cfg.ln_eps = 1e-5
-        x, y = _EdgeGatedConvFn.apply(
+        with torch.cuda.device(node_feats.device):     # kernels launch on the tensors' device, whatever the current one is
+            x, y = self._run_kernels(cfg, node_feats, edge_feats)
+        return x, (y if _need_edge_out else None)
+
+    def _run_kernels(self, cfg, node_feats, edge_feats):
+        return _EdgeGatedConvFn.apply(
             cfg, node_feats, edge_feats,
             self.src_gate.weight, self.src_gate.bias, self.dst_gate.weight, self.dst_gate.bias,
             self.edge_gate.weight, self.edge_gate.bias, self.src_update.weight, self.src_update.bias,
             self.dst_update.weight, self.dst_update.bias,
             self.bn_nodes.weight, self.bn_nodes.bias, self.bn_edges.weight, self.bn_edges.bias)
-        return x, (y if _need_edge_out else None)
 
 
 class ALIGNNConvBase(nn.Module):

@@ -307,6 +307,44 @@ __global__ void prepare_weights_kernel(const float* __restrict__ W, int N, int K
   *reinterpret_cast<uint4*>(img + chunk + F::B_PLANE + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
 }
 
+// Table-driven variant: every entry converts one source block into its place inside a (possibly larger) image, so
+// all operand images of a model -- [W_sg; W_du; W_dg; W_su] stacked along N, its transpose stacked along K, the
+// edge gate and its transpose, the embedding Linears (K zero-padded) -- are refreshed by ONE launch per step.
+// blockIdx.y = entry; thread = one 8-element K group of one image row inside the entry's block.
+__global__ void prepare_weights_table_kernel(const alignn_b200_image_entry* __restrict__ entries) {
+  const alignn_b200_image_entry e = entries[blockIdx.y];
+  const int Ne = e.transpose ? e.cols : e.rows, Ke = e.transpose ? e.rows : e.cols;   // block shape in image coordinates
+  const int k8n = (Ke + 7) / 8;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)Ne * k8n) return;
+  const int nl = (int)(t / k8n), k8 = (int)(t % k8n);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int kl = k8 * 8 + j;
+    v[j] = kl < Ke ? (e.transpose ? e.W[(int64_t)kl * e.ldw + nl] : e.W[(int64_t)nl * e.ldw + kl]) : 0.f;
+  }
+  uint2 h0, l0, h1, l1;
+  tc::split4(make_float4(v[0], v[1], v[2], v[3]), h0, l0);
+  tc::split4(make_float4(v[4], v[5], v[6], v[7]), h1, l1);
+  const int bn = (e.N % 256 == 0) ? 256 : (e.N % 128 == 0) ? 128 : (e.N % 64 == 0) ? 64 : 32;
+  const int n = e.n_off + nl, k = e.k_off + k8 * 8;          // image coordinates (k_off is a multiple of 8)
+  const int nt = n / bn, r = n % bn, kc = k / BK, kk = (k % BK) / 8;
+  const int64_t b_plane = (int64_t)bn * BK * 2;
+  const int64_t chunk = ((int64_t)nt * (e.K / BK) + kc) * 2 * b_plane;
+  const int off = plane_off(r, kk * 8);
+  uint8_t* img = reinterpret_cast<uint8_t*>(e.image);
+  *reinterpret_cast<uint4*>(img + chunk + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+  *reinterpret_cast<uint4*>(img + chunk + b_plane + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+}
+
+// dst[j] = a[j] (+ b[j]): the stacked / folded bias vectors that go with the images (blockIdx.y = entry)
+__global__ void prepare_bias_table_kernel(const alignn_b200_bias_entry* __restrict__ entries) {
+  const alignn_b200_bias_entry e = entries[blockIdx.y];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < e.n; j += gridDim.x * blockDim.x)
+    e.dst[j] = e.a[j] + (e.b ? e.b[j] : 0.f);
+}
+
 inline int pick_bn(int N) { return (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : (N % 32 == 0) ? 32 : 0; }
 
 template <int BN>
@@ -353,6 +391,24 @@ int alignn_b200_gemm_prepare_weights(const float* W, int N, int K, int64_t ldw, 
   else if (bn == 64) prepare_weights_kernel<64><<<blocks, 256, 0, st>>>(W, N, K, ldw, transpose, img);
   else prepare_weights_kernel<32><<<blocks, 256, 0, st>>>(W, N, K, ldw, transpose, img);
   return alignn::check_launch();
+}
+
+int alignn_b200_gemm_prepare_table(const alignn_b200_image_entry* entries, int n_entries, int64_t max_units,
+                                   const alignn_b200_bias_entry* bias_entries, int n_bias, alignn_stream_t stream) {
+  if (n_entries < 0 || n_bias < 0 || (n_entries > 0 && (!entries || max_units <= 0)) || (n_bias > 0 && !bias_entries))
+    return ALIGNN_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_entries > 0) {
+    const unsigned bx = (unsigned)((max_units + 255) / 256);
+    alignn::gemm::prepare_weights_table_kernel<<<dim3(bx, (unsigned)n_entries), 256, 0, st>>>(entries);
+    int rc = alignn::check_launch();
+    if (rc != ALIGNN_OK) return rc;
+  }
+  if (n_bias > 0) {
+    alignn::gemm::prepare_bias_table_kernel<<<dim3(4, (unsigned)n_bias), 256, 0, st>>>(bias_entries);
+    return alignn::check_launch();
+  }
+  return ALIGNN_OK;
 }
 
 int alignn_b200_gemm_nt(const float* A, int64_t lda, const void* w_image, int64_t M, int N, int K, const float* bias,

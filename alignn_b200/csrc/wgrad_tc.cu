@@ -11,6 +11,8 @@
 // TMEM (2 x 256 columns for D = 256), then writes its partial tile; a second kernel sums the partials
 // in a fixed order (deterministic, no float atomics).  Each input element is read from HBM exactly
 // once, which is the bound: the kernel moves 2*K*D*4 bytes.
+#include <cooperative_groups.h>
+
 #include "tc_common.cuh"
 #include "api_common.h"
 #include "alignn_b200.h"
@@ -46,7 +48,7 @@ struct Cfg {
 template <int DA, int DB>
 __global__ void __launch_bounds__(THREADS, 1)
 wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int64_t K,
-                    int rows_per_cta, float* __restrict__ partials) {
+                    int rows_per_cta, float* __restrict__ partials, float* __restrict__ out, int64_t ld_out) {
   using F = Cfg<DA, DB>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + F::PIPE);
@@ -201,6 +203,26 @@ wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __res
   tc::fence_before_sync();
   __syncthreads();
   if (warp == LOAD_WARPS) tc::tmem_dealloc(tmem, F::TMEM_COLS);
+  if (out) {
+    // Split-K reduction inside the kernel (cooperative launch: every CTA is resident): once all partial tiles are
+    // written, CTA c of a group sums its slice of the DA x DB output over the group's partials in a fixed order.
+    // Replaces a second launch that spent ~15 us walking the partials with 64 CTAs.
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    const int ctas = gridDim.x;
+    constexpr int64_t tile = (int64_t)DA * DB;
+    const float* p = partials + (int64_t)group * ctas * tile;
+    for (int64_t idx = ((int64_t)cta * THREADS + tid) * 4; idx < tile; idx += (int64_t)ctas * THREADS * 4) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+      for (int c = 0; c < ctas; ++c) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(p + (int64_t)c * tile + idx));
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      const int64_t o = idx / DB, i = idx % DB;
+      *reinterpret_cast<float4*>(out + ((int64_t)group * DA + o) * ld_out + i) = s;
+    }
+  }
 }
 
 // out[g*DA + o][i] = sum_c partials[g][c][o][i]  (fixed order)
@@ -241,7 +263,27 @@ int launch(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, 
   const int ctas = ctas_for(K, groups);
   int64_t rows = (K + ctas - 1) / ctas;
   rows = (rows + BK - 1) / BK * BK;               // slabs start on a stage boundary
-  wgrad_bf16x3_kernel<DA, DB><<<dim3(ctas, groups), THREADS, F::SMEM, st>>>(A, lda, B, ldb, K, (int)rows, ws);
+  // cooperative launch: ctas * groups <= 148 CTAs of one per SM, so the in-kernel grid barrier before the split-K
+  // reduction is legal; if the device cannot co-schedule them (MPS slice, smaller part) fall back to two launches
+  static int coop_ok = -1;
+  if (coop_ok < 0) {
+    int dev = 0, sms = 0, per_sm = 0, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wgrad_bf16x3_kernel<DA, DB>, THREADS, F::SMEM);
+    coop_ok = (coop && (int64_t)sms * per_sm >= kNumSMsWgrad) ? 1 : 0;
+  }
+  int rows_i = (int)rows;
+  if (coop_ok) {
+    float* ws_p = ws;
+    void* args[] = {(void*)&A, (void*)&lda, (void*)&B, (void*)&ldb, (void*)&K, (void*)&rows_i, (void*)&ws_p, (void*)&out, (void*)&ld_out};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)wgrad_bf16x3_kernel<DA, DB>, dim3(ctas, groups), dim3(THREADS), args,
+                                                (size_t)F::SMEM, st);
+    if (e != cudaSuccess) return record_cuda_error((int)e);
+    return check_launch();
+  }
+  wgrad_bf16x3_kernel<DA, DB><<<dim3(ctas, groups), THREADS, F::SMEM, st>>>(A, lda, B, ldb, K, rows_i, ws, nullptr, 0);
   int rc = check_launch();
   if (rc != ALIGNN_OK) return rc;
   const int64_t tile = (int64_t)DA * DB;

@@ -6,6 +6,7 @@ tensors or if the library reports an error -- there is no fallback path.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -29,14 +30,37 @@ class KernelTimer:
         return s, e
 
     def summary(self):
+        """name -> launches, total_ms, total algorithmic bytes; plus the same for the largest launches alone
+        (`big_*`: the L(g)-sized calls, bytes >= half of the largest)."""
         out = {}
         for name, rec in self.records.items():
             ms = [s.elapsed_time(e) for s, e, _ in rec]
-            out[name] = dict(launches=len(ms), avg_ms=sum(ms) / len(ms), bytes=rec[0][2])
+            by = [b for _, _, b in rec]
+            top = max(by)
+            big = [(m, b) for m, b in zip(ms, by) if 2 * b >= top]
+            out[name] = dict(launches=len(ms), total_ms=sum(ms), total_bytes=sum(by), big_launches=len(big),
+                             big_ms=sum(m for m, _ in big), big_bytes=sum(b for _, b in big))
         return out
 
 
 TIMER: Optional[KernelTimer] = None
+
+
+class _span:
+    """`with _span(name, nbytes): <library call>` -- CUDA events around the call on the launching stream when a
+    KernelTimer is installed (bench.py); free otherwise."""
+    __slots__ = ("ev",)
+
+    def __init__(self, name: str, nbytes: int):
+        self.ev = TIMER.span(name, int(nbytes)) if TIMER is not None else None
+
+    def __enter__(self):
+        if self.ev is not None:
+            self.ev[0].record()
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            self.ev[1].record()
 
 
 def _check_d(d: int) -> None:
@@ -82,17 +106,12 @@ def egc_forward(ix: EdgeIndex, x, y, G, P, n_w, n_b, e_w, e_b, *, norm_nodes: in
         x_out=ptr(x_out), y_out=ptr(y_out), M=None if gate_is_m else ptr(M), XP=ptr(XP), S=ptr(S), H=ptr(H),
         partials=ptr(partials),
         stream=stream_ptr())
-    span = None
-    if TIMER is not None and Ne >= TIMER.min_edges:
-        # compulsory bytes of THIS kernel: read G, P (each element once), indices; write what it writes
-        nb = 4 * d * (Ne + 4 * Nn) + 4 * Ne + 4 * (Nn + 1)
-        nb += 4 * d * Ne * (M is not None and not gate_is_m) + 4 * d * Nn * 3 * (XP is not None)
-        nb += 4 * d * Ne * (1 + int(residual)) * (y_out is not None) + 4 * d * Nn * (1 + int(residual)) * (x_out is not None)
-        span = TIMER.span("egc_forward_kernel" + ("<gate_is_m>" if gate_is_m else ""), nb)
-        span[0].record()
-    _lib.check(lib.alignn_b200_egc_forward(C.byref(a)), "alignn_b200_egc_forward")
-    if span is not None:
-        span[1].record()
+    # compulsory bytes of THIS kernel: read G (or m), P (each element once), indices; residual rows; what it writes
+    nb = 4 * d * (Ne + 4 * Nn) + 4 * Ne + 4 * (Nn + 1)
+    nb += 4 * d * Ne * (M is not None and not gate_is_m) + 4 * d * Nn * 3 * (XP is not None)
+    nb += 4 * d * Ne * (1 + int(residual)) * (y_out is not None) + 4 * d * Nn * (1 + int(residual)) * (x_out is not None)
+    with _span("egc_forward" + ("<gate_is_m>" if gate_is_m else ""), nb):
+        _lib.check(lib.alignn_b200_egc_forward(C.byref(a)), "alignn_b200_egc_forward")
     return dict(x_out=x_out, y_out=y_out, M=M, XP=XP, S=S, H=H, partials=partials)
 
 
@@ -115,8 +134,9 @@ def affine_silu_residual(R, res, scale, shift):
     _check_d(d)
     require_cuda(R, res, scale, shift)
     out = torch.empty_like(R)
-    _lib.check(lib.alignn_b200_affine_silu_residual(ptr(R), ptr(res), ptr(scale), ptr(shift), ptr(out), n, d,
-                                                     stream_ptr()), "alignn_b200_affine_silu_residual")
+    with _span("affine_silu_residual", 4 * n * d * (2 + (res is not None))):
+        _lib.check(lib.alignn_b200_affine_silu_residual(ptr(R), ptr(res), ptr(scale), ptr(shift), ptr(out), n, d,
+                                                         stream_ptr()), "alignn_b200_affine_silu_residual")
     return out
 
 
@@ -138,8 +158,9 @@ def bn_backward_reduce(R, g_out, scale, shift, mean, rstd) -> Tuple[torch.Tensor
     require_cuda(R, g_out, scale, shift, mean, rstd)
     rows = partial_rows(n, d)
     partials = torch.empty(rows, 2 * d, device=R.device, dtype=torch.float32)
-    _lib.check(lib.alignn_b200_bn_backward_reduce(ptr(R), ptr(g_out), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), n, d,
-                                                   ptr(partials), rows, stream_ptr()), "alignn_b200_bn_backward_reduce")
+    with _span("bn_backward_reduce", 8 * n * d):
+        _lib.check(lib.alignn_b200_bn_backward_reduce(ptr(R), ptr(g_out), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), n, d,
+                                                       ptr(partials), rows, stream_ptr()), "alignn_b200_bn_backward_reduce")
     c = colsum(partials, 1.0 / n)
     return c[:d], c[d:]
 
@@ -171,7 +192,10 @@ def egc_backward(ix: EdgeIndex, P, M, XP, S, H, gx_out, gy_out, n, e, *, norm_no
         n_c1=g(n, "c1"), n_c2=g(n, "c2"), e_c1=g(e, "c1"), e_c2=g(e, "c2"),
         gx_out=ptr(gx_out), gy_out=ptr(gy_out), GM=ptr(GM), GP=ptr(GP), GSh=ptr(GSh),
         partials=ptr(part), partials_src=ptr(part_src), stream=stream_ptr())
-    _lib.check(lib.alignn_b200_egc_backward(C.byref(a)), "alignn_b200_egc_backward")
+    # destination-keyed pass reads M, gy_out, node rows and writes GM, GP; source-keyed pass reads GM, M: SURVEY 8d
+    nb = 4 * d * (Ne * (2 + (gy_out is not None)) + 9 * Nn) + 12 * Ne + 4 * d * 2 * Ne
+    with _span("egc_backward(dst+src)", nb):
+        _lib.check(lib.alignn_b200_egc_backward(C.byref(a)), "alignn_b200_egc_backward")
     return GM, GP, colsum(part).view(6, d), colsum(part_src).view(2, d)
 
 
@@ -219,6 +243,16 @@ def segment_mean(x: torch.Tensor, graph_ptr: torch.Tensor) -> torch.Tensor:
     return _SegmentMean.apply(x.contiguous(), graph_ptr)
 
 
+def segment_mean_any_order(x: torch.Tensor, graph_ptr: torch.Tensor, second_order: bool) -> torch.Tensor:
+    """`segment_mean`, or (force training, which differentiates through the backward) the same pooling from torch operators."""
+    if not second_order:
+        return segment_mean(x, graph_ptr)
+    counts = (graph_ptr[1:] - graph_ptr[:-1]).long()
+    gid = torch.repeat_interleave(torch.arange(counts.numel(), device=x.device), counts, output_size=x.shape[0])
+    sums = torch.zeros(counts.numel(), x.shape[1], device=x.device, dtype=x.dtype).index_add(0, gid, x)
+    return sums / counts.clamp_min(1).to(x.dtype).unsqueeze(1)
+
+
 # ---- tensor-core Linear (tcgen05, bf16x3) --------------------------------------------------------
 class WeightImage:
     """bf16 hi/lo image of a weight matrix W[N,K] (or of W^T when transpose=True) in UMMA core-matrix
@@ -240,6 +274,131 @@ class WeightImage:
                                                         stream_ptr()), "alignn_b200_gemm_prepare_weights")
 
 
+class _Img:
+    """An operand image owned by an ImageTable (same attributes as WeightImage)."""
+    __slots__ = ("buf", "N", "K")
+
+    def __init__(self, N: int, K: int, device):
+        nbytes = int(_lib.load().alignn_b200_gemm_weight_image_bytes(N, K))
+        if nbytes == 0:
+            raise RuntimeError(f"alignn_b200 GEMM: unsupported weight shape N={N}, K={K} (need multiples of 32)")
+        self.N, self.K = N, K
+        self.buf = torch.zeros(nbytes, device=device, dtype=torch.uint8)     # zero: K padding stays zero forever
+
+
+class ImageTable:
+    """bf16 hi/lo operand images (and stacked / folded bias vectors) of a group of Linear layers, rebuilt by ONE
+    table-driven launch (`alignn_b200_gemm_prepare_table`) when -- and only when -- a source tensor changed
+    (storage pointer or autograd version).  Tables register their blocks once; a parent table (the model) absorbs
+    the tables of its layers so that a training step refreshes every image of the model in a single launch.
+
+    Inside a CUDA-graph capture the refresh of a table with trainable sources is always recorded: a captured training
+    step must rebuild its images on every replay, whatever the version counters said at capture time."""
+
+    def __init__(self, device=None):
+        self.device = device
+        self.images = {}
+        self.vectors = {}
+        self._blocks = []      # (image name, source tensor, transpose, n_off, k_off)
+        self._biases = []      # (vector name, offset, n, a, b)
+        self._children = []
+        self._parent = None
+        self._key = None
+        self._dev = None       # (entries tensor, n_entries, max_units, bias tensor, n_bias, pointer key)
+
+    # -- construction ---------------------------------------------------------------------------
+    def add_image(self, name: str, N: int, K: int, blocks, device):
+        """blocks: [(W, transpose, n_off, k_off)]; W is a 2-D fp32 tensor (a Linear weight)."""
+        self.images[name] = _Img(N, K, device)
+        for W, tr, n_off, k_off in blocks:
+            if k_off % 8:
+                raise RuntimeError("ImageTable: k_off must be a multiple of 8")
+            self._blocks.append((name, W, bool(tr), int(n_off), int(k_off)))
+        self._key = self._dev = None
+
+    def add_vector(self, name: str, n: int, parts, device):
+        """parts: [(offset, a, b_or_None)]: vector[offset : offset + len(a)] = a (+ b)."""
+        self.vectors[name] = torch.zeros(n, device=device, dtype=torch.float32)
+        for off, a, b in parts:
+            self._biases.append((name, int(off), int(a.numel()), a, b))
+        self._key = self._dev = None
+
+    def absorb(self, child: "ImageTable"):
+        self._children.append(child)
+        child._parent = weakref.ref(self)
+        self._key = self._dev = None
+
+    # -- refresh ----------------------------------------------------------------------------------
+    def _all(self):
+        out = [self]
+        for c in self._children:
+            out.extend(c._all())
+        return out
+
+    def _sources(self):
+        for t in self._all():
+            for _, W, _, _, _ in t._blocks:
+                yield W
+            for _, _, _, a, b in t._biases:
+                yield a
+                if b is not None:
+                    yield b
+
+    def _build_device_table(self):
+        ents, bias = [], []
+        max_units = 1
+        for t in self._all():
+            for name, W, tr, n_off, k_off in t._blocks:
+                if W.dim() != 2 or W.stride(1) != 1 or not W.is_cuda or W.dtype != torch.float32:
+                    raise RuntimeError("ImageTable: sources must be 2-D fp32 CUDA tensors with unit column stride")
+                img = t.images[name]
+                rows, cols = W.shape
+                n_img, k_img = (cols, rows) if tr else (rows, cols)
+                if n_off + n_img > img.N or k_off + (k_img + 7) // 8 * 8 > img.K:
+                    raise RuntimeError(f"ImageTable: block does not fit image {name}")
+                ents.append(_lib.ImageEntry(W=W.data_ptr(), ldw=W.stride(0), rows=rows, cols=cols, transpose=int(tr), n_off=n_off,
+                                            k_off=k_off, N=img.N, K=img.K, image=img.buf.data_ptr()))
+                max_units = max(max_units, n_img * ((k_img + 7) // 8))
+            for name, off, n, a, b in t._biases:
+                dst = t.vectors[name]
+                bias.append(_lib.BiasEntry(a=a.data_ptr(), b=None if b is None else b.data_ptr(),
+                                           dst=dst.data_ptr() + 4 * off, n=n))
+        dev = next(self._sources()).device
+
+        def pack(items, cls):
+            if not items:
+                return None
+            arr = (cls * len(items))(*items)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
+            self._host_keepalive.append(host)       # a captured copy reads this buffer again on every replay
+            return host.to(dev, non_blocking=True)
+        self._host_keepalive = []
+        self._dev = (pack(ents, _lib.ImageEntry), len(ents), max_units, pack(bias, _lib.BiasEntry), len(bias),
+                     tuple(s.data_ptr() for s in self._sources()))
+
+    def refresh(self):
+        """Rebuild the images if any source changed.  Returns True if a launch was issued."""
+        srcs = list(self._sources())
+        if not srcs:
+            return False
+        key = tuple((s.data_ptr(), s._version) for s in srcs)
+        capturing = torch.cuda.is_current_stream_capturing() and any(s.requires_grad for s in srcs)
+        if capturing and self._parent is not None and self._parent() is not None:
+            capturing = False                       # the model-level table records the refresh of all its layers
+        if key == self._key and not capturing:
+            return False
+        ptr_key = tuple(k[0] for k in key)
+        if self._dev is None or self._dev[5] != ptr_key:
+            self._build_device_table()
+        ents, n_e, max_units, bias, n_b, _ = self._dev
+        with torch.cuda.device(srcs[0].device):
+            _lib.check(_lib.load().alignn_b200_gemm_prepare_table(ptr_any(ents), n_e, max_units, ptr_any(bias), n_b, stream_ptr()),
+                       "alignn_b200_gemm_prepare_table")
+        for t in self._all():
+            t._key = tuple((s.data_ptr(), s._version) for s in t._sources())
+        return True
+
+
 def ptr_any(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -259,8 +418,9 @@ def gemm_nt(A: torch.Tensor, w: WeightImage, bias: Optional[torch.Tensor] = None
     ldr = residual.stride(0) if residual is not None else 0
     if residual is not None and (residual.stride(1) != 1 or residual.shape != (M, w.N)):
         raise RuntimeError("gemm_nt: bad residual layout")
-    _lib.check(lib.alignn_b200_gemm_nt(ptr_any(A), A.stride(0), ptr_any(w.buf), M, w.N, w.K, ptr_any(bias), ptr_any(residual),
-                                        ldr, ptr_any(out), out.stride(0), stream_ptr()), "alignn_b200_gemm_nt")
+    with _span(f"gemm_nt<{min(w.N, 256)}>", 4 * M * (w.K + w.N * (1 + (residual is not None)))):
+        _lib.check(lib.alignn_b200_gemm_nt(ptr_any(A), A.stride(0), ptr_any(w.buf), M, w.N, w.K, ptr_any(bias), ptr_any(residual),
+                                            ldr, ptr_any(out), out.stride(0), stream_ptr()), "alignn_b200_gemm_nt")
     return out
 
 
@@ -303,14 +463,10 @@ def gemm_gather(A: torch.Tensor, w: WeightImage, bias: Optional[torch.Tensor] = 
         add0=ptr_any(add0), ld0=add0.stride(0) if add0 is not None else 0, idx0=ptr_any(idx0),
         add1=ptr_any(add1), ld1=add1.stride(0) if add1 is not None else 0, idx1=ptr_any(idx1),
         C=ptr_any(out), ldc=out.stride(0), stats=ptr_any(part), stream=stream_ptr())
-    span = None
-    if TIMER is not None and M >= TIMER.min_edges:
-        nb = 4 * M * (w.K + w.N) + (8 * M if idx0 is not None else 0) + (4 * M * w.N if (add0 is not None and idx0 is None) else 0)
-        span = TIMER.span(f"gemm_gather<{w.N}>" + ("+gather" if idx0 is not None else "") + ("+res" if (add0 is not None and idx0 is None) else ""), nb)
-        span[0].record()
-    _lib.check(lib.alignn_b200_gemm_gather(C.byref(a)), "alignn_b200_gemm_gather")
-    if span is not None:
-        span[1].record()
+    nb = 4 * M * (w.K + w.N) + (8 * M if idx0 is not None else 0) + (4 * M * w.N if (add0 is not None and idx0 is None) else 0)
+    kind = "+gather" if idx0 is not None else ("+residual" if add0 is not None else "")
+    with _span(f"gemm_gather<{min(w.N, 256)}>" + kind + ("+stats" if stats else ""), nb):
+        _lib.check(lib.alignn_b200_gemm_gather(C.byref(a)), "alignn_b200_gemm_gather")
     return (out, part) if stats else out
 
 
@@ -331,8 +487,9 @@ def wgrad(A: torch.Tensor, B: torch.Tensor, groups: int = 1) -> torch.Tensor:
         raise RuntimeError(f"alignn_b200 wgrad: unsupported shape DA={DA}, DB={DB}")
     out = torch.empty(groups * DA, DB, device=A.device, dtype=torch.float32)
     ws = torch.empty(max(nbytes, 16), device=A.device, dtype=torch.uint8)
-    _lib.check(lib.alignn_b200_wgrad(ptr(A), A.stride(0), ptr(B), B.stride(0), K, DA, DB, groups, ptr(out), DB, ptr_any(ws),
-                                      nbytes, stream_ptr()), "alignn_b200_wgrad")
+    with _span(f"wgrad<{DA},{DB}>", 4 * K * (groups * DA + DB)):
+        _lib.check(lib.alignn_b200_wgrad(ptr(A), A.stride(0), ptr(B), B.stride(0), K, DA, DB, groups, ptr(out), DB, ptr_any(ws),
+                                          nbytes, stream_ptr()), "alignn_b200_wgrad")
     return out
 
 
@@ -348,29 +505,44 @@ def colsum_rows(a: torch.Tensor) -> torch.Tensor:
     return colsum(part)
 
 
+def linear_table(lin) -> ImageTable:
+    """Images of one nn.Linear (weight zero-padded along K to a multiple of 32) and of its transpose, cached on the module."""
+    dev = lin.weight.device
+    tbl = getattr(lin, "_alignn_b200_images", None)
+    if tbl is not None and tbl.device == dev:
+        return tbl
+    k_pad = (lin.in_features + 31) // 32 * 32
+    tbl = ImageTable(dev)
+    tbl.add_image("w", lin.out_features, k_pad, [(lin.weight, False, 0, 0)], dev)
+    tbl.add_image("wT", k_pad, lin.out_features, [(lin.weight, True, 0, 0)], dev)
+    object.__setattr__(lin, "_alignn_b200_images", tbl)
+    return tbl
+
+
+def _pad_cols(x: torch.Tensor, k_pad: int) -> torch.Tensor:
+    x = x.contiguous()
+    return x if x.shape[1] == k_pad else torch.nn.functional.pad(x, (0, k_pad - x.shape[1]))
+
+
 class _TCLinearFn(torch.autograd.Function):
     """y = x W^T + b on the tcgen05 bf16x3 GEMMs (forward, data gradient, weight gradient)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, k_pad):
-        x = x.contiguous()
-        if k_pad != x.shape[1]:
-            x = torch.nn.functional.pad(x, (0, k_pad - x.shape[1]))
-            w = torch.nn.functional.pad(weight, (0, k_pad - weight.shape[1]))
-        else:
-            w = weight.contiguous()
-        ctx.save_for_backward(x, w)
+    def forward(ctx, x, weight, bias, tbl):
+        x = _pad_cols(x, tbl.images["w"].K)
+        ctx.save_for_backward(x)
+        ctx.tbl = tbl
         ctx.k_in = weight.shape[1]
-        return gemm_nt(x, WeightImage(w), bias.contiguous())
+        return gemm_gather(x, tbl.images["w"], bias.contiguous())
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, go):
-        x, w = ctx.saved_tensors
+        (x,) = ctx.saved_tensors
         go = go.contiguous()
         gx = None
         if ctx.needs_input_grad[0]:
-            gx = gemm_nt(go, WeightImage(w, transpose=True))[:, :ctx.k_in]
+            gx = gemm_gather(go, ctx.tbl.images["wT"])[:, :ctx.k_in]
         gw = wgrad(go, x, 1)[:, :ctx.k_in]
         gb = colsum_rows(go)
         return gx, gw, gb, None
@@ -381,10 +553,11 @@ def tc_linear_supported(in_features: int, out_features: int) -> bool:
     return out_features in _lib.SUPPORTED_D and wgrad_supported(out_features, k_pad)
 
 
-def tc_linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+def tc_linear(x: torch.Tensor, lin) -> torch.Tensor:
     """nn.Linear forward/backward on the tensor-core kernels; the input width is zero-padded to a multiple of 32."""
-    k_pad = (weight.shape[1] + 31) // 32 * 32
-    return _TCLinearFn.apply(x, weight, bias, k_pad)
+    tbl = linear_table(lin)
+    tbl.refresh()
+    return _TCLinearFn.apply(x, lin.weight, lin.bias, tbl)
 
 
 # ---- Linear -> BatchNorm1d(train) -> SiLU (embedding MLP layers) ------------------------------------
@@ -393,16 +566,10 @@ class _MLPBNTrainFn(torch.autograd.Function):
     statistics (fp64 finalize + running-stat update), fused normalise+SiLU, and the matching backward."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, bn, k_pad):
-        lib = _lib.load()
-        x = x.contiguous()
-        if k_pad != x.shape[1]:
-            x = torch.nn.functional.pad(x, (0, k_pad - x.shape[1]))
-            w = torch.nn.functional.pad(weight, (0, k_pad - weight.shape[1]))
-        else:
-            w = weight.contiguous()
+    def forward(ctx, x, weight, bias, gamma, beta, bn, tbl):
+        x = _pad_cols(x, tbl.images["w"].K)
         # Linear + per-channel batch statistics in one pass (column sums leave through the GEMM epilogue)
-        R, part = gemm_gather(x, WeightImage(w), bias.contiguous(), stats=True)
+        R, part = gemm_gather(x, tbl.images["w"], bias.contiguous(), stats=True)
         n, d = R.shape
         track = bn.track_running_stats and bn.running_mean is not None
         scale, shift, mean, rstd = bn_finalize(part, 0, n, gamma.contiguous(), beta.contiguous(), bn.eps, float(bn.momentum),
@@ -410,7 +577,8 @@ class _MLPBNTrainFn(torch.autograd.Function):
         if track and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
         out = affine_silu_residual(R, None, scale, shift)
-        ctx.save_for_backward(x, w, R, scale, shift, mean, rstd)
+        ctx.save_for_backward(x, R, scale, shift, mean, rstd)
+        ctx.tbl = tbl
         ctx.k_in = weight.shape[1]
         return out
 
@@ -418,22 +586,24 @@ class _MLPBNTrainFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, go):
         lib = _lib.load()
-        x, w, R, scale, shift, mean, rstd = ctx.saved_tensors
+        x, R, scale, shift, mean, rstd = ctx.saved_tensors
         go = go.contiguous()
         n, d = R.shape
         c1, c2 = bn_backward_reduce(R, go, scale, shift, mean, rstd)
         gR = torch.empty_like(R)
-        _lib.check(lib.alignn_b200_bn_backward_apply(ptr(R), ptr(go), ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
-                                                     ptr(c1.contiguous()), ptr(c2.contiguous()), n, d, ptr(gR), stream_ptr()),
-                   "alignn_b200_bn_backward_apply")
+        with _span("bn_backward_apply", 12 * n * d):
+            _lib.check(lib.alignn_b200_bn_backward_apply(ptr(R), ptr(go), ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
+                                                         ptr(c1.contiguous()), ptr(c2.contiguous()), n, d, ptr(gR), stream_ptr()),
+                       "alignn_b200_bn_backward_apply")
         gx = None
         if ctx.needs_input_grad[0]:
-            gx = gemm_nt(gR, WeightImage(w, transpose=True))[:, :ctx.k_in]
+            gx = gemm_gather(gR, ctx.tbl.images["wT"])[:, :ctx.k_in]
         gw = wgrad(gR, x, 1)[:, :ctx.k_in]
         # a bias that feeds a train-mode BatchNorm has an identically zero gradient (sum_rows gR == 0)
         return gx, gw, torch.zeros_like(c1), c2 * n, c1 * n, None, None
 
 
 def mlp_bn_train(x, lin, bn):
-    k_pad = (lin.in_features + 31) // 32 * 32
-    return _MLPBNTrainFn.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, bn, k_pad)
+    tbl = linear_table(lin)
+    tbl.refresh()
+    return _MLPBNTrainFn.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, bn, tbl)

@@ -77,21 +77,15 @@ def peaks():
 # CPU oracle arm (cpu_baseline and --impl reference)
 # ---------------------------------------------------------------------------------------------
 def _oracle_setup(args, graphs):
-    from alignn_b200 import synthetic
+    """One fwd+bwd+AdamW step of the oracle on `graphs` crystals.  Inputs come from oracle/synthetic_inputs.py (the same
+    generator as the product's, restated with oracle types): nothing of alignn_b200 is imported on this arm."""
     from oracle import alignn_oracle as O
-    g, lg, lat, tgt = synthetic.make_batch(batch_size=graphs, atoms=args.atoms, k=12, seed=123)
-
-    def to_o(gr):
-        s, d = gr.edges()
-        og = O.OGraph(s.long(), d.long(), gr.num_nodes(), gr.batch_num_nodes(), gr.batch_num_edges())
-        og.ndata.update(gr.ndata)
-        og.edata.update(gr.edata)
-        return og
+    from oracle import synthetic_inputs as SI
+    og, olg, lat, tgt = SI.make_batch(batch_size=graphs, atoms=args.atoms, k=12, seed=123)
     torch.manual_seed(123)
     model = O.ALIGNN(norm=args.norm)
     model.train()
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
-    og, olg = to_o(g), to_o(lg)
 
     def step():
         opt.zero_grad(set_to_none=True)
@@ -102,12 +96,12 @@ def _oracle_setup(args, graphs):
     return step
 
 
-def cpu_calibrate(args):
-    """Pick the host thread count the oracle runs fastest with (more threads is not faster for these
-    gather/index_add-heavy ops on a 100+ core box) and a per-step sample size of about 4 s."""
+def cpu_calibrate(args, graphs):
+    """Host thread count the oracle runs fastest with, measured on the SAME `graphs`-crystal step that is then timed
+    (more threads is not faster for these gather/index_add-heavy ops on a 100+ core box)."""
     ncpu = os.cpu_count() or 1
-    cands = sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)})
-    step = _oracle_setup(args, 2)
+    cands = sorted({min(ncpu, c) for c in (16, 32, 64)})
+    step = _oracle_setup(args, graphs)
     best = None
     for th in cands:
         torch.set_num_threads(th)
@@ -117,9 +111,7 @@ def cpu_calibrate(args):
         dt = time.perf_counter() - t0
         if best is None or dt < best[1]:
             best = (th, dt)
-    threads, t2 = best
-    graphs = int(max(1, min(args.batch, round(4.0 / (t2 / 2)))))
-    return threads, graphs
+    return best[0]
 
 
 def cpu_oracle_run(args, graphs, steps, warmup, threads):
@@ -140,20 +132,20 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads, graphs = cpu_calibrate(args)
-    if args.cpu_sample_graphs > 0:
-        graphs = args.cpu_sample_graphs
+    graphs = args.cpu_sample_graphs if args.cpu_sample_graphs > 0 else args.batch     # the full 64-graph batch by default
+    threads = cpu_calibrate(args, graphs)
     gps, ms = cpu_oracle_run(args, graphs, args.steps, max(1, min(args.warmup, 3)), threads)
-    cores = threads
     line = {
         "impl": "reference", "metric": METRIC, "value": gps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{graphs} graphs per step (bounded CPU sample of the 64-graph batch)",
-                   "norm": args.norm},
-        "cpu_baseline": {"value": gps, "unit": UNIT, "cores": cores, "kind": "port",
+        "config": {"workload": WORKLOAD, "model": "ALIGNN 4+4 d=256 (" + args.norm + ", train mode)",
+                   "global_batch": graphs, "per_gpu_batch": graphs, "parallelism": "cpu", "optimizer": "AdamW", "loss": "L1",
+                   "sample": f"{graphs} graphs per step" + ("" if graphs == args.batch else " (bounded CPU sample of the 64-graph batch)")},
+        "cpu_baseline": {"value": gps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps x {graphs} graphs, torch-CPU restatement of the reference DGL path "
-                                   f"(DGL is not installable offline); thread count calibrated over {os.cpu_count()} cores"},
+                                   f"(DGL is not installable offline); thread count calibrated on the same step over "
+                                   f"{os.cpu_count()} cores"},
         "e2e": {"value": gps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -174,7 +166,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -274,33 +266,50 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # everything below (warm-up, capture, every timed region) runs on ONE side stream: the autograd accumulators are
+    # created on the stream that later replays them
+    work = torch.cuda.Stream()
+    work.wait_stream(torch.cuda.current_stream())
+
     def timed(fn, steps):
+        """EXACTLY `steps` calls between two events on the launching stream, barrier + synchronize on both sides,
+        max over ranks."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
+        with torch.cuda.stream(work):
+            e0.record()
+            for i in range(steps):
+                fn(i)
+            e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    # ---- warm-up (also builds the flat gradient buffer) ----------------------------------------
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
+    def timed_repeats(fn, steps, budget_s=2.5, max_reps=10):
+        """Median of up to `max_reps` repetitions of exactly `steps` steps (the clock sampler needs seconds, a 20-step
+        region lasts ~0.2 s); every repetition is a full timed region as above."""
+        first = timed(fn, steps)
+        reps = int(max(1, min(max_reps, budget_s * 1e3 / max(first, 1e-3))))
+        if world > 1:
+            t = torch.tensor([reps], device=dev)
+            dist.broadcast(t, 0)
+            reps = int(t.item())
+        all_ms = [first] + [timed(fn, steps) for _ in range(reps - 1)]
+        return statistics.median(all_ms), all_ms
+
+    # ---- warm-up (also builds the flat gradient buffer and the operand-image tables) ------------
+    with torch.cuda.stream(work):
         for i in range(max(args.warmup, 3)):
             step(resident[i % nb])
-    torch.cuda.current_stream().wait_stream(side)
     barrier()
 
     # ---- CUDA graphs: one per resident batch and one per host batch (H2D copies inside the graph) --------
-    # The step is ~650 launches of which most are small (g-graph convs, norms, optimizer); replaying them as a
-    # graph removes the host launch cost.  Shapes are static here; a real variable-size loader would bucket.
-    # The gradient all-reduce stays OUTSIDE the graphs (an NCCL collective inside a captured graph hung on this
-    # stack): per step = replay(zero_grad + forward + backward) -> eager flat all-reduce -> replay(optimizer).
+    # The step is a few hundred launches of which most are small (g-graph convs, norms, optimizer); replaying them as
+    # a graph removes the host launch cost.  Shapes are static here; a variable-size loader buckets (DESIGN.md).
+    # The gradient all-reduce stays OUTSIDE the graphs: per step = replay(zero_grad + forward + backward) -> eager flat
+    # all-reduce -> replay(optimizer).
     graphs_res, graphs_e2e, graph_opt, launches_per_step = [], [], None, None
 
     def fwd_bwd(batch):
@@ -317,18 +326,18 @@ def run_ours(args):
         for b in range(nb):
             gr = torch.cuda.CUDAGraph()
             l0 = _lib.launch_count()
-            with torch.cuda.graph(gr, pool=pool):
+            with torch.cuda.graph(gr, pool=pool, stream=work):
                 loss_b = fwd_bwd(resident[b])
             launches_per_step = _lib.launch_count() - l0
             pool = pool or gr.pool()
             graphs_res.append((gr, loss_b))
         for b in range(nb):
             gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr, pool=pool):
+            with torch.cuda.graph(gr, pool=pool, stream=work):
                 loss_b = fwd_bwd(h2d(b))
             graphs_e2e.append((gr, loss_b))
         graph_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph_opt, pool=pool):
+        with torch.cuda.graph(graph_opt, pool=pool, stream=work):
             opt.step()
         barrier()
 
@@ -349,28 +358,31 @@ def run_ours(args):
             return loss_b.item()                              # D2H + sync, as train.py:300-305 does
         return step(h2d(i)).item()
 
-    for i in range(2):
-        run_resident(i)
+    with torch.cuda.stream(work):
+        for i in range(2):
+            run_resident(i)
 
     # ---- timed: resident inputs -------------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count()
-    ms_total = timed(run_resident, args.steps)
-    launches = (launches_per_step * args.steps) if use_graph else (_lib.launch_count() - l0)
+    ms_total, reps_res = timed_repeats(run_resident, args.steps)
+    launches = (launches_per_step * args.steps) if use_graph else ((_lib.launch_count() - l0) // max(len(reps_res), 1))
 
     # ---- timed: end to end from pinned host memory, loss read back every step ----------------
-    for i in range(2):
-        run_e2e(i)
-    ms_e2e = timed(run_e2e, args.steps)
+    with torch.cuda.stream(work):
+        for i in range(2):
+            run_e2e(i)
+    ms_e2e, reps_e2e = timed_repeats(run_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- dominant kernel: CUDA events around every L(g) launch of the fused edge kernel, eager replay of
-    #      the same steps (events inside a graph replay carry no timestamps) ------------------------------
-    for i in range(2):                                        # eager allocations settle on this stream
-        step(resident[i % nb])
-    ops.TIMER = ops.KernelTimer(min_edges=T // 2)
+    # ---- per-kernel table: CUDA events around every library call in an eager replay of the same steps (events inside
+    #      a graph replay carry no timestamps); the roofline entry is the kernel with the largest total time ----------
+    with torch.cuda.stream(work):
+        for i in range(2):                                    # eager allocations settle on this stream
+            step(resident[i % nb])
+    ops.TIMER = ops.KernelTimer()
     ms_eager = timed(lambda i: step(resident[i % nb]), args.steps)
     ksum = ops.TIMER.summary()
     ops.TIMER = None
@@ -390,16 +402,30 @@ def run_ours(args):
     d = cfg.hidden_features
     sbytes = step_bytes(N, E, T, d, cfg.alignn_layers, cfg.gcn_layers)
     ms_step = ms_total / args.steps
-    k = ksum.get("egc_forward_kernel")
+    traffic_tab = {}
+    tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")     # dram bytes per launch from `ncu --set full` captures
+    if os.path.exists(tpath) and args.norm == "batchnorm" and (N, E, T) == (1920, 23040, 276480):
+        with open(tpath) as fh:
+            traffic_tab = json.load(fh)
+
+    def entry(name, k):
+        # the kernel's L(g)-sized launches: algorithmic bytes / event time
+        ach = k["big_bytes"] / (k["big_ms"] * 1e-3) / 1e9 if k["big_ms"] > 0 else 0.0
+        tr = traffic_tab.get(name)
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_source": (tr or {}).get("source"),
+                "share_of_eager_step": k["total_ms"] / ms_eager, "ms_per_step": k["total_ms"] / args.steps,
+                "launches_per_step": k["launches"] / args.steps, "big_launches_per_step": k["big_launches"] / args.steps,
+                "avg_big_launch_ms": k["big_ms"] / max(k["big_launches"], 1),
+                "algorithmic_bytes_per_big_launch": k["big_bytes"] / max(k["big_launches"], 1)}
+    table = sorted((entry(n, k) for n, k in ksum.items()), key=lambda e: -e["ms_per_step"])
     roofline = None
-    if k:
-        ach = k["bytes"] / (k["avg_ms"] * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture per round
-        # (profiles/r01_ncu_full_summary.md: 383.6 + 302.6 MB in BatchNorm-train mode); unknown for other modes
-        traffic = 686.2e6 if args.norm == "batchnorm" and (N, E, T) == (1920, 23040, 276480) else None
-        roofline = {"bound": "hbm", "kernel": "egc_forward_kernel<256> on L(g) (Nn=E, Ne=T)", "achieved": ach,
-                    "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                    "avg_launch_ms": k["avg_ms"], "launches_timed": k["launches"], "algorithmic_bytes_per_launch": k["bytes"]}
+    if table:
+        roofline = dict(table[0])
+        roofline["peak_source"] = peak_src
+        roofline["note"] = ("dominant kernel by total time in the step; achieved = algorithmic bytes (DESIGN.md section 4) of its "
+                            "L(g)-sized launches / CUDA-event time on the launching stream")
+        roofline["extra"] = table[1:8]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -408,24 +434,27 @@ def run_ours(args):
                    "global_batch": graphs_per_step, "per_gpu_batch": args.batch, "N": N, "E": E, "T": T,
                    "parallelism": f"dp{world}", "optimizer": "AdamW(fused)", "loss": "L1",
                    "cuda_graph": use_graph, "eager_ms_per_step": ms_eager / args.steps,
+                   "timing": f"median of {len(reps_res)} repetitions of exactly {args.steps} steps (each: events on the launching "
+                             f"stream, barrier + synchronize on both sides, max over ranks)",
+                   "repetition_ms": [round(m, 3) for m in reps_res],
                    "l2": f"no explicit flush: per-step working set ~{sbytes / 1e9:.1f} GB >> 126 MB L2; 4 batches rotate"},
         "roofline": roofline,
         "step_hbm": {"algorithmic_bytes_per_step": sbytes, "achieved": sbytes / (ms_step * 1e-3) / 1e9, "peak": peak,
                      "unit": "GB/s", "frac": sbytes / (ms_step * 1e-3) / 1e9 / peak,
                      "note": "conv-stack compulsory bytes per batch (SURVEY 8d) / whole step time incl. embeddings, GEMMs, optimizer"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4, "repetition_ms": [round(m, 3) for m in reps_e2e]},
         "gpu_launches": int(lt.item()),
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
-        threads, graphs = cpu_calibrate(args)
-        if args.cpu_sample_graphs > 0:
-            graphs = args.cpu_sample_graphs
-        gps, ms = cpu_oracle_run(args, graphs, 3, 1, threads)
+        # bounded sample of the same workload on the host cores: the full 64-graph step, fixed thread count
+        threads = min(32, os.cpu_count() or 1)
+        gps, ms = cpu_oracle_run(args, args.batch if args.cpu_sample_graphs <= 0 else args.cpu_sample_graphs, 2, 1, threads)
         line["cpu_baseline"] = {"value": gps, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"3 steps x {graphs} graphs (fwd+bwd+AdamW), torch-CPU restatement of the reference "
-                                          f"DGL path; thread count calibrated over the box's {os.cpu_count()} cores"}
+                                "sample": f"2 steps x {args.batch if args.cpu_sample_graphs <= 0 else args.cpu_sample_graphs} graphs "
+                                          f"(fwd+bwd+AdamW) after 1 warm-up, torch-CPU restatement of the reference DGL path, "
+                                          f"{threads} threads of the box's {os.cpu_count()} cores"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -215,6 +215,23 @@ int alignn_b200_gather_segment_sum(const float* Bh, const float* sigma, const in
 size_t alignn_b200_gemm_weight_image_bytes(int N, int K);   /* 0 if the shape is unsupported */
 int alignn_b200_gemm_prepare_weights(const float* W, int N, int K, int64_t ldw, int transpose, void* image,
                                      alignn_stream_t stream);
+/* Table-driven refresh of many operand images in one launch (+ one for the bias vectors).  Every entry converts one
+ * source block W[rows, cols] (row stride ldw; transpose != 0: the block enters as its transpose) into the image of an
+ * [N, K] operand at row offset n_off / column offset k_off (k_off % 8 == 0; blocks narrower than a multiple of 8 are
+ * zero-padded).  Typical use: [src_gate; dst_update; dst_gate; src_update] stacked along N for the node projections,
+ * the same four transposed and stacked along K for their data gradient (alignn.py:98,99,104,110).  The entry arrays live
+ * in DEVICE memory (the caller builds them once; parameter storage is stable across optimizer steps).
+ * max_units >= max over entries of image_rows * ceil(image_cols_of_block / 8). */
+typedef struct {
+  const float* W; int64_t ldw;
+  int32_t rows, cols, transpose;
+  int32_t n_off, k_off;
+  int32_t N, K;
+  void* image;
+} alignn_b200_image_entry;
+typedef struct { const float* a; const float* b; float* dst; int32_t n; } alignn_b200_bias_entry;   /* dst = a (+ b) */
+int alignn_b200_gemm_prepare_table(const alignn_b200_image_entry* entries, int n_entries, int64_t max_units,
+                                   const alignn_b200_bias_entry* bias_entries, int n_bias, alignn_stream_t stream);
 int alignn_b200_gemm_nt(const float* A, int64_t lda, const void* w_image, int64_t M, int N, int K, const float* bias,
                         const float* R, int64_t ldr, float* C, int64_t ldc, alignn_stream_t stream);
 

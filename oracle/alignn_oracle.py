@@ -279,7 +279,7 @@ def cutoff_envelope(r, inner_cutoff=4, exponent=3):
 
 def energy_and_forces(model: ALIGNN, g: OGraph, lg: OGraph, energy_mult_natoms=True, use_penalty=True,
                       penalty_factor=0.1, penalty_threshold=1.0, use_cutoff_function=False, multiply_cutoff=False,
-                      inner_cutoff=3.0, exponent=5):
+                      inner_cutoff=3.0, exponent=5, create_graph=False):
     """Energy + per-atom forces the ALIGNN-FF way (alignn_atomwise.py:404-467,495-510,526-563).
 
     r requires grad; cosines recomputed from r inside the autograd graph (lg_on_fly);
@@ -312,12 +312,14 @@ def energy_and_forces(model: ALIGNN, g: OGraph, lg: OGraph, energy_mult_natoms=T
         en = en + pen.sum()
         if not energy_mult_natoms:
             out = en                                  # the in-place `en_out += total_penalty` on the alias of `out`
-    (dr,) = torch.autograd.grad(en.sum(), r)
+    (dr,) = torch.autograd.grad(en.sum(), r, create_graph=create_graph)   # create_graph=True: force training (:530-539)
     pair_forces = -dr
     zeros = torch.zeros(g.n, 3, dtype=r.dtype)
     f_ji = zeros.index_add(0, g.dst, pair_forces)     # copy_e/sum on g           (:547-550)
     f_ij = zeros.index_add(0, g.src, pair_forces)     # copy_e/sum on reverse(g)  (:555-562)
     # result['out'] is the un-multiplied per-graph output (alignn_atomwise.py:653); en_out drives forces
+    if create_graph:
+        return out, f_ji - f_ij, pair_forces
     return out.detach(), (f_ji - f_ij).detach(), pair_forces.detach()
 
 

@@ -86,3 +86,69 @@ def test_cutoff_and_penalty_tails_match_reference(golden_dir, cpu_pool, tag, cfg
     res = _cpu_model(**cfg)((g, lg, lat))
     np.testing.assert_allclose(res["out"].detach().numpy(), gold[tag + ".out"], rtol=1e-7, atol=1e-8)
     np.testing.assert_allclose(res["grad"].numpy(), gold[tag + ".forces"], rtol=1e-7, atol=1e-8)
+
+
+# ---- force TRAINING: double backward through the torch-operator composition (conv.second_order) --------------------
+class _TorchOpsLayer(torch.nn.Module):
+    """The product layer run through `conv._torch_ops_forward` (what `second_order` selects on the GPU), on the CPU."""
+
+    def __init__(self, layer, kind):
+        super().__init__()
+        self.layer, self.kind = layer, kind
+
+    def forward(self, g, *args, **kw):
+        from alignn_b200 import conv
+        if self.kind == "gcn":
+            x, y = args
+            return conv._torch_ops_forward(self.layer, g.index, x, y, kw.get("_need_edge_out", True))
+        lg, x, y, z = args
+        x, m = conv._torch_ops_forward(self.layer.node_update, g.index, x, y, True)
+        y, z = conv._torch_ops_forward(self.layer.edge_update, lg.index, m, z, kw.get("_need_z_out", True))
+        return x, y, z
+
+
+def test_force_training_gradients_match_oracle_double_backward(cpu_pool):
+    """d(force loss + energy loss)/d(parameters) through create_graph=True (alignn_atomwise.py:530-539) agrees with the
+    oracle's double backward: the force term really trains (it silently did not)."""
+    g, lg, lat = _batch()
+    m = A.ALIGNNAtomWise(A.ALIGNNAtomWiseConfig(name="alignn_atomwise", alignn_layers=2, gcn_layers=2, hidden_features=32,
+                                                embedding_features=32, atom_input_features=92)).double().train()
+    GI.fill_state_dict(m, 77)
+    orc = O.ALIGNN(norm="layernorm", alignn_layers=2, gcn_layers=2, hidden_features=32, embedding_features=32).double().train()
+    orc.load_state_dict(m.state_dict())
+    m.alignn_layers = torch.nn.ModuleList([_TorchOpsLayer(l, "alignn") for l in m.alignn_layers])
+    m.gcn_layers = torch.nn.ModuleList([_TorchOpsLayer(l, "gcn") for l in m.gcn_layers])
+    res = m((g, lg, lat))
+    assert res["grad"].requires_grad                       # the forces stay in the autograd graph in training
+    tgt_f = GI.features(12, g.num_nodes(), 3).double()
+    loss = (res["grad"] - tgt_f).abs().mean() + res["out"].abs().mean()
+    loss.backward()
+    out, forces, _ = O.energy_and_forces(orc, to_oracle(g), to_oracle(lg), create_graph=True)
+    ref = (forces - tgt_f).abs().mean() + out.abs().mean()
+    ref.backward()
+    got = {k.replace(".layer.", ".", 1) if False else k: v for k, v in m.named_parameters()}
+    n_checked = 0
+    for name, p_ref in orc.named_parameters():
+        name_m = name
+        for pre in ("alignn_layers.", "gcn_layers."):
+            if name.startswith(pre):
+                i, rest = name[len(pre):].split(".", 1)
+                name_m = f"{pre}{i}.layer.{rest}"
+        p = dict(m.named_parameters())[name_m]
+        if p_ref.grad is None:
+            assert p.grad is None or p.grad.abs().max() == 0
+            continue
+        assert p.grad is not None, name
+        scale = max(p_ref.grad.abs().max().item(), 1e-12)
+        assert (p.grad - p_ref.grad).abs().max().item() <= 1e-7 * scale + 1e-14, name
+        n_checked += 1
+    assert n_checked > 30
+    # the force term contributes: a conv weight's gradient differs from the energy-only gradient
+    assert dict(m.named_parameters())["gcn_layers.0.layer.src_gate.weight"].grad.abs().max() > 0
+
+
+def test_property_only_config_skips_the_force_pass():
+    """alignn_atomwise.py:267-268: gradwise_weight == 0 switches calculate_gradient off (works under no_grad)."""
+    cfg = A.ALIGNNAtomWiseConfig(name="alignn_atomwise", gradwise_weight=0.0)
+    m = A.ALIGNNAtomWise(cfg)
+    assert m.config.calculate_gradient is False

@@ -246,3 +246,20 @@ def test_conv_two_formulations_agree():
     x2 = x + torch.nn.functional.silu(conv.bn_nodes(conv.src_update(x) + h))
     y2 = y + torch.nn.functional.silu(conv.bn_edges(m))
     assert torch.allclose(xo, x2, rtol=1e-12, atol=1e-12) and torch.allclose(yo, y2, rtol=1e-12, atol=1e-12)
+
+
+def test_oracle_only_synthetic_batch_equals_the_product_generator():
+    """bench.py's CPU reference arm builds its inputs without importing the product: same graphs, same features."""
+    from alignn_b200 import synthetic
+    from oracle import synthetic_inputs as SI
+    g, lg, lat, tgt = synthetic.make_batch(batch_size=3, atoms=9, k=12, seed=31)
+    og, olg, olat, otgt = SI.make_batch(batch_size=3, atoms=9, k=12, seed=31)
+    s, d = g.edges()
+    assert torch.equal(s.long(), og.src) and torch.equal(d.long(), og.dst)
+    assert torch.equal(g.ndata["atom_features"], og.ndata["atom_features"]) and torch.equal(g.edata["r"], og.edata["r"])
+    assert torch.equal(lat, olat) and torch.equal(tgt, otgt)
+    # L(g): same edge SET (the product emits destination-major, the oracle source-major) with the same cosines
+    ls, ld = lg.edges()
+    a = sorted(zip(ls.tolist(), ld.tolist(), lg.edata["h"].tolist()))
+    b = sorted(zip(olg.src.tolist(), olg.dst.tolist(), olg.edata["h"].tolist()))
+    assert a == b
