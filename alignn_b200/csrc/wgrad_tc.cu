@@ -159,19 +159,23 @@ wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __res
     const int c_begin = halves ? (warp >> 2) * (DB / 2) : 0;
     const int c_end = (F::MT == 2) ? DB : (halves ? c_begin + DB / 2 : ((warp >> 2) == 0 ? DB : 0));
     const int o = mt * 128 + row_in_tile;
+    // Partial tiles are a private workspace, stored BLOCKED: element (o, c) at ((c / 32) * DA + o) * 32 + c % 32, so that
+    // the row-per-thread accumulator fragments leave as 128 contiguous bytes per lane and 4 KB per warp instruction
+    // (row-major would scatter every store over 32 lines).  The reduction below un-blocks.
     if (nk > 0) {
       for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         float v[32];
         tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * DB + c0), v);
         if (o < DA) {
+          float* dst = out + ((int64_t)(c0 >> 5) * DA + o) * 32;
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(out + (int64_t)o * DB + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
       }
     } else if (o < DA) {
       for (int c0 = c_begin; c0 < c_end; c0 += 4)
-        *reinterpret_cast<float4*>(out + (int64_t)o * DB + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(out + ((int64_t)(c0 >> 5) * DA + o) * 32 + (c0 & 31)) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   } else if (lane == 0) {
     // ================= MMA issuer =================
@@ -213,13 +217,22 @@ wgrad_bf16x3_kernel(const float* __restrict__ A, int64_t lda, const float* __res
     constexpr int64_t tile = (int64_t)DA * DB;
     const float* p = partials + (int64_t)group * ctas * tile;
     for (int64_t idx = ((int64_t)cta * THREADS + tid) * 4; idx < tile; idx += (int64_t)ctas * THREADS * 4) {
+      // 16 partials per batch: the loads of a batch are independent (latency paid once per batch), the adds keep one
+      // fixed order
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-      for (int c = 0; c < ctas; ++c) {
+      int c = 0;
+      for (; c + 16 <= ctas; c += 16) {
+        float4 v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(p + (int64_t)(c + u) * tile + idx));
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+      }
+      for (; c < ctas; ++c) {
         const float4 v = __ldcg(reinterpret_cast<const float4*>(p + (int64_t)c * tile + idx));
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       }
-      const int64_t o = idx / DB, i = idx % DB;
+      const int64_t o = (idx >> 5) % DA, i = (idx >> 5) / DA * 32 + (idx & 31);     // blocked -> row-major
       *reinterpret_cast<float4*>(out + ((int64_t)group * DA + o) * ld_out + i) = s;
     }
   }
@@ -237,7 +250,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partials, int ctas
     const float4 v = __ldcs(reinterpret_cast<const float4*>(p + (int64_t)c * tile));
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
-  const int64_t o = idx / DB, i = idx % DB;
+  const int64_t o = (idx >> 5) % DA, i = (idx >> 5) / DA * 32 + (idx & 31);         // blocked -> row-major (see the epilogue)
   *reinterpret_cast<float4*>(out + ((int64_t)g * DA + o) * ld_out + i) = s;
 }
 
@@ -245,7 +258,9 @@ inline int ctas_for(int64_t K, int groups) {
   int per_group = kNumSMsWgrad / groups;
   if (per_group < 1) per_group = 1;
   const int64_t chunks = (K + BK - 1) / BK;
-  const int64_t want = (chunks + 3) / 4;          // at least ~4 pipeline stages of work per CTA (fewer, larger slabs measured no faster)
+  // every CTA writes (and the reduction re-reads) a full DA x DB partial tile -- 256 KB at D = 256 -- so a short
+  // reduction is not spread thinner than 4 pipeline chunks (128 rows) per CTA.
+  const int64_t want = (chunks + 3) / 4;
   if (want < per_group) per_group = (int)(want < 1 ? 1 : want);
   return per_group;
 }

@@ -125,6 +125,44 @@ class FlatGradAllReducer:
             self._work = None
 
 
+class FlatAdamW:
+    """AdamW over ONE flat parameter: the parameters that receive gradients (`reducer.active`, discovered on the first
+    backward) are re-homed as views into one contiguous fp32 buffer, their gradients already live in the reducer's
+    flat buffer, so the whole update is a single fused multi-tensor launch (the per-tensor fused AdamW needs ~10 launches
+    of ~40 us for ALIGNN's 87 small tensors).  Same arithmetic as `torch.optim.AdamW` per element; parameters without
+    gradients are untouched, as with the per-parameter optimizer.
+
+    After an eager step the autograd version of every parameter is bumped, so caches keyed on it (operand images,
+    alignn_b200.ops.ImageTable) see the update; inside a CUDA-graph capture those caches refresh unconditionally."""
+
+    def __init__(self, reducer: FlatGradAllReducer, lr: float = 1e-3, capturable: bool = False, **kw):
+        if reducer.flat is None:
+            raise RuntimeError("FlatAdamW: run one backward() and reducer.gather() first (discovers the trainable set)")
+        self.reducer = reducer
+        self.params = list(reducer.active)
+        flat = torch.empty_like(reducer.flat)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                n = p.numel()
+                flat[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = flat[off:off + n].view_as(p)
+                off += n
+        self.flat_param = torch.nn.Parameter(flat)
+        self.flat_param.grad = reducer.flat
+        self.opt = torch.optim.AdamW([self.flat_param], lr=lr, fused=flat.is_cuda, capturable=capturable and flat.is_cuda, **kw)
+
+    def step(self):
+        self.flat_param.grad = self.reducer.flat
+        self.opt.step()
+        if not (self.flat_param.is_cuda and torch.cuda.is_current_stream_capturing()):
+            for p in self.params:
+                torch.autograd.graph.increment_version(p)
+
+    def zero_grad(self):
+        self.reducer.zero_grad()
+
+
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:
     """Make every rank start from rank `src`'s parameters and buffers (what DDP does at wrap time)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

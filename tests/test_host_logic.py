@@ -255,3 +255,39 @@ def test_native_line_graph_is_the_definition_on_any_multigraph(gr):
     ls, lt = (a.numpy() for a in lg.edges())
     assert list(zip(ls.tolist(), lt.tolist())) == want
     assert lg.num_nodes() == src.size
+
+
+def test_flat_adamw_equals_per_parameter_adamw():
+    """dp.FlatAdamW (one flat parameter, one fused launch on the GPU) performs the same update as torch.optim.AdamW
+    on the individual tensors; parameters that never receive a gradient stay untouched; versions are bumped."""
+    from alignn_b200 import dp
+    torch.manual_seed(0)
+
+    def make():
+        torch.manual_seed(1)
+        return torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.SiLU(), torch.nn.Linear(5, 3), torch.nn.Linear(3, 3))
+    a, b = make(), make()
+    x, y = torch.randn(16, 6), torch.randn(16, 3)
+
+    def loss(m):
+        return (m[2](m[1](m[0](x))) - y).abs().mean()          # m[3] never used: no gradient, like the dead norm layers
+    ref_opt = torch.optim.AdamW(a.parameters(), lr=1e-2)
+    red = dp.FlatGradAllReducer(b.parameters())
+    red.zero_grad()
+    loss(b).backward()
+    red.gather()
+    opt = dp.FlatAdamW(red, lr=1e-2)
+    dead_before = b[3].weight.detach().clone()
+    for _ in range(4):
+        ref_opt.zero_grad(set_to_none=True)
+        loss(a).backward()
+        ref_opt.step()
+        red.zero_grad()
+        loss(b).backward()
+        v0 = b[0].weight._version
+        red.all_reduce()
+        opt.step()
+        assert b[0].weight._version > v0
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-7)
+    assert torch.equal(b[3].weight, dead_before)
