@@ -113,6 +113,16 @@ _SIGNATURES = {
     "alignn_b200_radius_graph_count_host": (C.c_int64, [_fp, _fp, C.c_int64, C.c_int64, C.c_double, C.c_double]),
     "alignn_b200_radius_graph_build_host": (C.c_int, [_fp, _fp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int64, _fp,
                                                       _fp, _fp, _fp]),
+    "alignn_b200_csr_build_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "alignn_b200_csr_build": (C.c_int, [_fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
+    "alignn_b200_line_graph_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "alignn_b200_line_graph_offsets": (C.c_int, [_fp, _fp, _fp, C.c_int64, _fp, _fp, C.c_size_t, _fp]),
+    "alignn_b200_line_graph_fill": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp, _fp, _fp, _fp]),
+    "alignn_b200_radius_graph_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "alignn_b200_radius_graph_offsets": (C.c_int, [_fp, _fp, C.c_int64, C.c_int64, C.c_double, C.c_double, _fp, _fp, C.c_size_t, _fp]),
+    "alignn_b200_radius_graph_fill": (C.c_int, [_fp, _fp, C.c_int64, C.c_int64, C.c_double, C.c_double, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "alignn_b200_pair_force_scatter": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, _fp, _fp]),
+    "alignn_b200_virial_stress": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_float, _fp, _fp]),
     "alignn_b200_segment_mean": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, _fp, _fp]),
     "alignn_b200_segment_mean_backward": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, _fp, _fp]),
 }

@@ -240,16 +240,25 @@ class ALIGNNAtomWise(nn.Module):
             pair_forces = c.grad_multiplier * dr                         # (:530-539)
             if c.force_mult_natoms:
                 pair_forces = pair_forces * g.num_nodes()
-            src, dst = g.index.src.long(), g.index.dst.long()
-            zeros = torch.zeros(g.num_nodes(), 3, device=r.device, dtype=r.dtype)
-            forces = zeros.index_add(0, dst, pair_forces)                # copy_e/sum over in-edges (:547-550)
-            if c.add_reverse_forces:
-                forces = forces - zeros.index_add(0, src, pair_forces)   # ... minus over out-edges (:555-563)
+            if second or not pair_forces.is_cuda:
+                # force training: the reductions stay differentiable torch operators
+                src, dst = g.index.src.long(), g.index.dst.long()
+                zeros = torch.zeros(g.num_nodes(), 3, device=r.device, dtype=r.dtype)
+                forces = zeros.index_add(0, dst, pair_forces)                # copy_e/sum over in-edges (:547-550)
+                if c.add_reverse_forces:
+                    forces = forces - zeros.index_add(0, src, pair_forces)   # ... minus over out-edges (:555-563)
+            else:
+                # inference / MD: one deterministic kernel for both reductions (csrc/graph_device.cu)
+                forces = ops.pair_force_scatter(pair_forces, g.index, c.add_reverse_forces)
             forces = torch.squeeze(forces)
             result["pair_forces"] = pair_forces
             if c.stresswise_weight != 0:
-                stress = virial_stress(r if second else r.detach(), pair_forces, g.node_graph_offsets(), g.batch_num_edges(),
-                                       g.ndata["V"], c.stress_multiplier)
+                if second or not pair_forces.is_cuda:
+                    stress = virial_stress(r if second else r.detach(), pair_forces, g.node_graph_offsets(),
+                                           g.batch_num_edges(), g.ndata["V"], c.stress_multiplier)
+                else:
+                    stress = ops.virial_stress(r.detach(), pair_forces, g.edge_graph_offsets64(),
+                                               g.node_graph_offsets().long(), g.ndata["V"], c.stress_multiplier)
         if c.link == "log":
             out = torch.exp(out)
         elif c.link == "logit":

@@ -1,16 +1,16 @@
-// STAGED WORK (see graph_device.h): device-side structure builders and the force / stress reductions of SURVEY.md
-// section 8f -- the GPU twins of csrc/graph_host.cu (sorted-CSR index, line graph) and of the torch index_add tails in
-// alignn_b200/alignn_atomwise.py.  Pure integer work except the two d=3 reductions; everything deterministic
+// Device-side structure builders and the force / stress reductions of SURVEY.md section 8f -- the GPU twins of
+// csrc/graph_host.cu (sorted-CSR index, line graph, periodic radius scan; bit-identical outputs, validated on B200) and
+// the d=3 reductions of ALIGNN-FF (alignn/models/alignn_atomwise.py:547-563, 610-635).  Pure integer work except the two d=3 reductions; everything deterministic
 // (stable radix sort, fixed-order sums, integer atomics only for counting).  CUB (ships with the CUDA toolkit) does
 // the scans and the stable key-value sort; it is plumbing here, like cudart.
 #include <cub/cub.cuh>
 #include <stdint.h>
 
+#include "api_common.h"
 #include "alignn_b200.h"
-#include "graph_device.h"
 
 namespace alignn {
-namespace staged {
+namespace device {
 
 constexpr int kBlock = 256;
 inline int blocks_for(int64_t n) { return (int)((n + kBlock - 1) / kBlock); }
@@ -75,7 +75,7 @@ int csr_one(const int32_t* key, int64_t Nn, int64_t E, int32_t* ptr, int32_t* ei
     b = w.cub_bytes;
     cub::DeviceRadixSort::SortPairs(w.cub, b, key, w.keys, w.iota, eid, (int)E, 0, key_bits(Nn), st);   // LSD radix: stable
   }
-  return cudaGetLastError() == cudaSuccess ? ALIGNN_OK : ALIGNN_ERR_CUDA;
+  return alignn::check_launch();
 }
 
 // ---- line graph ---------------------------------------------------------------------------------
@@ -201,20 +201,20 @@ virial_stress_kernel(const float* __restrict__ r, const float* __restrict__ pf, 
   if (threadIdx.x < 9) out[9 * b + threadIdx.x] = factor * red[0][threadIdx.x] / V[node_off[b]];   // first atom's volume
 }
 
-}  // namespace staged
+}  // namespace device
 }  // namespace alignn
 
 extern "C" {
 
 size_t alignn_b200_csr_build_workspace_bytes(int64_t num_nodes, int64_t num_edges) {
   if (num_nodes < 0 || num_edges < 0 || num_nodes >= ((int64_t)1 << 31) - 1 || num_edges >= ((int64_t)1 << 31)) return 0;
-  return alignn::staged::csr_ws(nullptr, num_nodes, num_edges).total;
+  return alignn::device::csr_ws(nullptr, num_nodes, num_edges).total;
 }
 
 int alignn_b200_csr_build(const int32_t* src, const int32_t* dst, int64_t num_nodes, int64_t num_edges, int32_t* in_ptr,
                           int32_t* in_eid, int32_t* out_ptr, int32_t* out_eid, int32_t* flags, void* workspace,
-                          size_t workspace_bytes, void* stream) {
-  using namespace alignn::staged;
+                          size_t workspace_bytes, alignn_stream_t stream) {
+  using namespace alignn::device;
   if (num_nodes < 0 || num_edges < 0 || num_nodes >= ((int64_t)1 << 31) - 1 || num_edges >= ((int64_t)1 << 31)) return ALIGNN_ERR_BAD_ARG;
   if (!in_ptr || !out_ptr || !flags || !workspace || (num_edges > 0 && (!src || !dst || !in_eid || !out_eid))) return ALIGNN_ERR_BAD_ARG;
   const CsrWs w = csr_ws(workspace, num_nodes, num_edges);
@@ -232,12 +232,12 @@ size_t alignn_b200_line_graph_workspace_bytes(int64_t num_edges) {
   if (num_edges < 0 || num_edges >= ((int64_t)1 << 31) - 1) return 0;
   size_t scan_b = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, scan_b, (const int32_t*)nullptr, (int32_t*)nullptr, (int)(num_edges + 1));
-  return alignn::staged::align256((size_t)(num_edges + 1) * 4) + alignn::staged::align256(scan_b);
+  return alignn::device::align256((size_t)(num_edges + 1) * 4) + alignn::device::align256(scan_b);
 }
 
 int alignn_b200_line_graph_offsets(const int32_t* src, const int32_t* dst, const int32_t* in_ptr, int64_t num_edges,
-                                   int32_t* offsets, void* workspace, size_t workspace_bytes, void* stream) {
-  using namespace alignn::staged;
+                                   int32_t* offsets, void* workspace, size_t workspace_bytes, alignn_stream_t stream) {
+  using namespace alignn::device;
   if (num_edges < 0 || num_edges >= ((int64_t)1 << 31) - 1 || !offsets || !workspace) return ALIGNN_ERR_BAD_ARG;
   if (num_edges > 0 && (!src || !dst || !in_ptr)) return ALIGNN_ERR_BAD_ARG;
   if (workspace_bytes < alignn_b200_line_graph_workspace_bytes(num_edges)) return ALIGNN_ERR_WORKSPACE;
@@ -247,31 +247,31 @@ int alignn_b200_line_graph_offsets(const int32_t* src, const int32_t* dst, const
   size_t b = workspace_bytes - align256((size_t)(num_edges + 1) * 4);
   lg_count_kernel<<<blocks_for(num_edges + 1), kBlock, 0, st>>>(src, dst, in_ptr, num_edges, cnt);
   cub::DeviceScan::ExclusiveSum(cubws, b, cnt, offsets, (int)(num_edges + 1), st);      // offsets[E] = T; also L(g)'s in_ptr
-  return cudaGetLastError() == cudaSuccess ? ALIGNN_OK : ALIGNN_ERR_CUDA;
+  return alignn::check_launch();
 }
 
 int alignn_b200_line_graph_fill(const int32_t* src, const int32_t* dst, const int32_t* in_ptr, const int32_t* in_eid,
-                                int64_t num_edges, const int32_t* offsets, int32_t* lsrc, int32_t* ldst, void* stream) {
-  using namespace alignn::staged;
+                                int64_t num_edges, const int32_t* offsets, int32_t* lsrc, int32_t* ldst, alignn_stream_t stream) {
+  using namespace alignn::device;
   if (num_edges < 0) return ALIGNN_ERR_BAD_ARG;
   if (num_edges == 0) return ALIGNN_OK;
   if (!src || !dst || !in_ptr || !in_eid || !offsets || !lsrc || !ldst) return ALIGNN_ERR_BAD_ARG;
   lg_fill_kernel<<<blocks_for(num_edges * 32), kBlock, 0, (cudaStream_t)stream>>>(src, dst, in_ptr, in_eid, num_edges, offsets,
                                                                                 lsrc, ldst);
-  return cudaGetLastError() == cudaSuccess ? ALIGNN_OK : ALIGNN_ERR_CUDA;
+  return alignn::check_launch();
 }
 
 size_t alignn_b200_radius_graph_workspace_bytes(int64_t num_atoms) {
   if (num_atoms < 0 || num_atoms >= ((int64_t)1 << 31) - 1) return 0;
   size_t scan_b = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, scan_b, (const int32_t*)nullptr, (int32_t*)nullptr, (int)(num_atoms + 1));
-  return alignn::staged::align256((size_t)(num_atoms + 1) * 4) + alignn::staged::align256(scan_b);
+  return alignn::device::align256((size_t)(num_atoms + 1) * 4) + alignn::device::align256(scan_b);
 }
 
 int alignn_b200_radius_graph_offsets(const double* cart_coords, const double* shifts, int64_t num_atoms, int64_t num_images,
                                      double cutoff, double atol, int32_t* offsets, void* workspace, size_t workspace_bytes,
-                                     void* stream) {
-  using namespace alignn::staged;
+                                     alignn_stream_t stream) {
+  using namespace alignn::device;
   if (num_atoms < 0 || num_images < 0 || !offsets || !workspace || (num_atoms > 0 && !cart_coords) || (num_images > 0 && !shifts))
     return ALIGNN_ERR_BAD_ARG;
   if (workspace_bytes < alignn_b200_radius_graph_workspace_bytes(num_atoms)) return ALIGNN_ERR_WORKSPACE;
@@ -284,43 +284,43 @@ int alignn_b200_radius_graph_offsets(const double* cart_coords, const double* sh
     radius_scan_kernel<false><<<blocks_for(num_atoms * 32), kBlock, 0, st>>>(cart_coords, shifts, num_atoms, num_images, cutoff,
                                                                           atol, nullptr, cnt, nullptr, nullptr, nullptr, nullptr);
   cub::DeviceScan::ExclusiveSum(cubws, b, cnt, offsets, (int)(num_atoms + 1), st);     // offsets[N] = number of bonds
-  return cudaGetLastError() == cudaSuccess ? ALIGNN_OK : ALIGNN_ERR_CUDA;
+  return alignn::check_launch();
 }
 
 int alignn_b200_radius_graph_fill(const double* cart_coords, const double* shifts, int64_t num_atoms, int64_t num_images,
                                   double cutoff, double atol, const int32_t* offsets, int32_t* u, int32_t* v,
-                                  int32_t* image_index, float* r, void* stream) {
-  using namespace alignn::staged;
+                                  int32_t* image_index, float* r, alignn_stream_t stream) {
+  using namespace alignn::device;
   if (num_atoms < 0 || num_images < 0) return ALIGNN_ERR_BAD_ARG;
   if (num_atoms == 0) return ALIGNN_OK;
   if (!cart_coords || (num_images > 0 && !shifts) || !offsets || !u || !v || !image_index || !r) return ALIGNN_ERR_BAD_ARG;
   radius_scan_kernel<true><<<blocks_for(num_atoms * 32), kBlock, 0, (cudaStream_t)stream>>>(
       cart_coords, shifts, num_atoms, num_images, cutoff, atol, offsets, nullptr, u, v, image_index, r);
-  return cudaGetLastError() == cudaSuccess ? ALIGNN_OK : ALIGNN_ERR_CUDA;
+  return alignn::check_launch();
 }
 
 int alignn_b200_pair_force_scatter(const float* pair_forces, const int32_t* in_ptr, const int32_t* in_eid,
                                    const int32_t* out_ptr, const int32_t* out_eid, int64_t num_nodes, int add_reverse,
-                                   float* forces, void* stream) {
-  using namespace alignn::staged;
+                                   float* forces, alignn_stream_t stream) {
+  using namespace alignn::device;
   if (num_nodes < 0) return ALIGNN_ERR_BAD_ARG;
   if (num_nodes == 0) return ALIGNN_OK;
   if (!pair_forces || !in_ptr || !forces || (add_reverse && (!out_ptr || !out_eid))) return ALIGNN_ERR_BAD_ARG;
   pair_force_scatter_kernel<<<blocks_for(num_nodes), kBlock, 0, (cudaStream_t)stream>>>(pair_forces, in_ptr, in_eid, out_ptr,
                                                                                          out_eid, num_nodes, add_reverse, forces);
-  return cudaGetLastError() == cudaSuccess ? ALIGNN_OK : ALIGNN_ERR_CUDA;
+  return alignn::check_launch();
 }
 
 int alignn_b200_virial_stress(const float* r, const float* pair_forces, const int64_t* edge_offsets,
                               const int64_t* node_offsets, const float* V, int64_t batch_size, float multiplier,
-                              float* stress, void* stream) {
-  using namespace alignn::staged;
+                              float* stress, alignn_stream_t stream) {
+  using namespace alignn::device;
   if (batch_size < 0) return ALIGNN_ERR_BAD_ARG;
   if (batch_size == 0) return ALIGNN_OK;
   if (!r || !pair_forces || !edge_offsets || !node_offsets || !V || !stress) return ALIGNN_ERR_BAD_ARG;
   virial_stress_kernel<<<(int)batch_size, kBlock, 0, (cudaStream_t)stream>>>(r, pair_forces, edge_offsets, node_offsets, V,
                                                                             -160.21766208f * multiplier, stress);
-  return cudaGetLastError() == cudaSuccess ? ALIGNN_OK : ALIGNN_ERR_CUDA;
+  return alignn::check_launch();
 }
 
 }  // extern "C"

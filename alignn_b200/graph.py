@@ -71,6 +71,30 @@ class EdgeIndex:
         return EdgeIndex(t(s32), t(d32), t(in_ptr), t(in_eid), t(out_ptr), t(out_eid),
                          bool(flags[0]), int(flags[1]), num_nodes)
 
+    @staticmethod
+    def build_device(src: torch.Tensor, dst: torch.Tensor, num_nodes: int) -> "EdgeIndex":
+        """The same index built ON THE GPU from int32 CUDA tensors (alignn_b200_csr_build: integer histogram, scan,
+        stable radix sort of edge ids; bit-identical to `build`).  One 8-byte read-back (dst_sorted, max in-degree)."""
+        from . import _lib
+        lib = _lib.load()
+        if not (src.is_cuda and dst.is_cuda):
+            raise RuntimeError("EdgeIndex.build_device needs CUDA tensors")
+        src = src.to(torch.int32).contiguous()
+        dst = dst.to(torch.int32).contiguous()
+        E, dev = src.numel(), src.device
+        i32 = lambda n: torch.empty(n, device=dev, dtype=torch.int32)  # noqa: E731
+        in_ptr, out_ptr, in_eid, out_eid, flags = i32(num_nodes + 1), i32(num_nodes + 1), i32(E), i32(E), i32(2)
+        nb = int(lib.alignn_b200_csr_build_workspace_bytes(num_nodes, E))
+        if nb == 0:
+            raise ValueError("graph too large for int32 edge index")
+        ws = torch.empty(nb, device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            _lib.check(lib.alignn_b200_csr_build(src.data_ptr(), dst.data_ptr(), num_nodes, E, in_ptr.data_ptr(), in_eid.data_ptr(),
+                                                 out_ptr.data_ptr(), out_eid.data_ptr(), flags.data_ptr(), ws.data_ptr(), nb,
+                                                 _lib.stream_ptr()), "alignn_b200_csr_build")
+        f = flags.tolist()
+        return EdgeIndex(src, dst, in_ptr, in_eid, out_ptr, out_eid, bool(f[0]), int(f[1]), num_nodes)
+
     _FIELDS = ("src", "dst", "in_ptr", "in_eid", "out_ptr", "out_eid")
 
     def to(self, device, non_blocking=False) -> "EdgeIndex":
@@ -101,10 +125,15 @@ class Graph:
     def __init__(self, src=None, dst=None, num_nodes: Optional[int] = None,
                  batch_num_nodes=None, batch_num_edges=None, *, _index: Optional[EdgeIndex] = None):
         if _index is None:
-            src, dst = _np(src).reshape(-1), _np(dst).reshape(-1)
-            if num_nodes is None:
-                num_nodes = int(max(src.max(), dst.max())) + 1 if src.size else 0
-            _index = EdgeIndex.build(src, dst, int(num_nodes))
+            if isinstance(src, torch.Tensor) and src.is_cuda and num_nodes is not None:
+                # edges already on the GPU (device-side neighbour list / line graph): build the index there
+                _index = EdgeIndex.build_device(src.reshape(-1), torch.as_tensor(dst, device=src.device).reshape(-1),
+                                                int(num_nodes))
+            else:
+                src, dst = _np(src).reshape(-1), _np(dst).reshape(-1)
+                if num_nodes is None:
+                    num_nodes = int(max(src.max(), dst.max())) + 1 if src.size else 0
+                _index = EdgeIndex.build(src, dst, int(num_nodes))
         self.index = _index
         self._n = _index.num_nodes
         E = int(_index.src.numel())
@@ -205,6 +234,8 @@ class Graph:
         from . import _lib
         lib = _lib.load()
         ix = self.index
+        if self.device.type == "cuda":
+            return self._line_graph_device(shared)
         src = np.ascontiguousarray(ix.src.cpu().numpy())
         in_ptr = np.ascontiguousarray(ix.in_ptr.cpu().numpy())
         in_eid = np.ascontiguousarray(ix.in_eid.cpu().numpy())
@@ -224,6 +255,44 @@ class Graph:
         if shared:
             lg.ndata.update(self.edata)
         return lg
+
+
+    def _line_graph_device(self, shared: bool) -> "Graph":
+        """L(g) built on the GPU (alignn_b200_line_graph_offsets / _fill + alignn_b200_csr_build): same edge list as the
+        host builder, bit for bit.  One small read-back (T and the per-crystal pair counts) sizes the outputs."""
+        from . import _lib
+        lib = _lib.load()
+        ix, dev, E = self.index, self.device, self.num_edges()
+        off = torch.empty(E + 1, device=dev, dtype=torch.int32)
+        nb = int(lib.alignn_b200_line_graph_workspace_bytes(E))
+        ws = torch.empty(max(nb, 1), device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr()
+            _lib.check(lib.alignn_b200_line_graph_offsets(ix.src.data_ptr(), ix.dst.data_ptr(), ix.in_ptr.data_ptr(), E,
+                                                          off.data_ptr(), ws.data_ptr(), nb, st), "alignn_b200_line_graph_offsets")
+            eoff = torch.zeros(self._bne.numel() + 1, dtype=torch.int64)
+            eoff[1:] = torch.cumsum(self._bne, 0)
+            at = off[eoff.to(dev)].tolist()                      # pairs before each crystal's first bond; last = T
+            T = int(at[-1])
+            lsrc, ldst = (torch.empty(T, device=dev, dtype=torch.int32) for _ in range(2))
+            _lib.check(lib.alignn_b200_line_graph_fill(ix.src.data_ptr(), ix.dst.data_ptr(), ix.in_ptr.data_ptr(),
+                                                       ix.in_eid.data_ptr(), E, off.data_ptr(), lsrc.data_ptr(), ldst.data_ptr(), st),
+                       "alignn_b200_line_graph_fill")
+        lbne = torch.tensor([b - a for a, b in zip(at[:-1], at[1:])], dtype=torch.int64)
+        lg = Graph(lsrc, ldst, E, self._bne.clone(), lbne)
+        if shared:
+            lg.ndata.update(self.edata)
+        return lg
+
+    def edge_graph_offsets64(self) -> torch.Tensor:
+        """int64 [B+1] prefix of batch_num_edges on this graph's device (per-crystal edge ranges, virial stress)."""
+        t = getattr(self, "_eoff64", None)
+        if t is None or t.device != self.device:
+            t = torch.zeros(self._bne.numel() + 1, dtype=torch.int64)
+            t[1:] = torch.cumsum(self._bne, 0)
+            t = t.to(self.device)
+            self._eoff64 = t
+        return t
 
 
 # ---- module-level helpers mirroring dgl.* ------------------------------------
@@ -279,22 +348,26 @@ def as_graph(g) -> Graph:
     """Accept our Graph, or anything DGLGraph-like (edges/num_nodes/batch_num_* /ndata/edata)."""
     if isinstance(g, Graph):
         return g
-    cached = getattr(g, "_alignn_b200_graph", None)
-    if cached is not None:
-        return cached
     if not (hasattr(g, "edges") and hasattr(g, "num_nodes")):
         raise TypeError(f"expected alignn_b200.Graph or a DGLGraph-like object, got {type(g)!r}")
-    s, d = g.edges()
-    out = Graph(s, d, g.num_nodes(), g.batch_num_nodes(), g.batch_num_edges())
-    dev = s.device if isinstance(s, torch.Tensor) else torch.device("cpu")
-    if dev.type != "cpu":
-        out = out.to(dev)
+    # only the STRUCTURE (sorted-CSR index) is cached on the foreign object; features are taken from the live object
+    # on every call, so updated edata / ndata (MD, relaxation, augmentation) are never stale
+    cached = getattr(g, "_alignn_b200_graph", None)
+    if cached is None:
+        s, d = g.edges()
+        cached = Graph(s, d, g.num_nodes(), g.batch_num_nodes(), g.batch_num_edges())
+        dev = s.device if isinstance(s, torch.Tensor) else torch.device("cpu")
+        if dev.type != "cpu" and cached.device != dev:
+            cached = cached.to(dev)
+        try:
+            g._alignn_b200_graph = cached
+        except Exception:
+            pass
+    out = cached.local_var()
+    out.ndata.clear()
+    out.edata.clear()
     out.ndata.update(dict(g.ndata))
     out.edata.update(dict(g.edata))
-    try:
-        g._alignn_b200_graph = out
-    except Exception:
-        pass
     return out
 
 

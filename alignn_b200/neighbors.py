@@ -14,8 +14,8 @@ This is the input side of the hot path for real structures and for BASELINE conf
      search repeated (the reference tests `dgl.graph((u, v)).num_nodes() == len(atoms)`).
 
 Both directions of a bond appear (as two separate rows, NOT adjacent: this builder emits source-major order),
-multi-edges to different images and self-image bonds occur.  The device-side version of this builder is a
-"next" row of SURVEY.md section 8f; this host version is what feeds `Graph` today.
+multi-edges to different images and self-image bonds occur.  `radius_graph_device` / `crystal_graph_device` run the
+same scan (and the index / line-graph construction) on the GPU with bit-identical results.
 """
 from __future__ import annotations
 
@@ -26,6 +26,64 @@ import numpy as np
 import torch
 
 from .graph import Graph, bond_cosines
+
+
+def radius_graph_device(lattice_mat, cart_coords, cutoff: float = 5.0, bond_tol: float = 0.5, atol: float = 1e-5,
+                        cutoff_extra: float = 0.5, device="cuda"):
+    """`radius_graph` with the distance scan ON THE GPU (alignn_b200_radius_graph_offsets / _fill: one warp per atom,
+    double precision with the host builder's operation order): identical bonds in identical order and identical fp32
+    displacement vectors, returned as CUDA tensors (u int32, v int32, r float32 [E,3], image_index int32) plus the
+    [I,3] cell table -- what an MD loop needs to rebuild g and L(g) every step without leaving the device
+    (alignn/ff/calculators.py:284-291 rebuilds them on the CPU)."""
+    from . import _lib
+    lib = _lib.load()
+    dev = torch.device(device)
+    lat = np.asarray(lattice_mat, dtype=np.float64)
+    X = np.asarray(cart_coords, dtype=np.float64)
+    n = X.shape[0]
+    frac = X @ np.linalg.inv(lat)
+    Xd = torch.from_numpy(np.ascontiguousarray(X)).to(dev)
+    while True:
+        recp = 2 * math.pi * np.linalg.inv(lat).T
+        recp_len = np.sqrt((recp ** 2).sum(1))
+        maxr = np.ceil((cutoff + bond_tol) * recp_len / (2 * math.pi))
+        nmin = np.floor(frac.min(0)) - maxr
+        nmax = np.ceil(frac.max(0)) + maxr
+        ranges = [np.arange(a, b, dtype=np.float64) for a, b in zip(nmin, nmax)]
+        cells = np.stack(np.meshgrid(*ranges, indexing="ij"), -1).reshape(-1, 3)
+        sh = torch.from_numpy(np.ascontiguousarray(cells @ lat)).to(dev)
+        off = torch.empty(n + 1, device=dev, dtype=torch.int32)
+        nb = int(lib.alignn_b200_radius_graph_workspace_bytes(n))
+        ws = torch.empty(max(nb, 1), device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr()
+            _lib.check(lib.alignn_b200_radius_graph_offsets(Xd.data_ptr(), sh.data_ptr(), n, sh.shape[0], float(cutoff), float(atol),
+                                                            off.data_ptr(), ws.data_ptr(), nb, st), "alignn_b200_radius_graph_offsets")
+            E = int(off[-1].item())
+            u, v, ci = (torch.empty(E, device=dev, dtype=torch.int32) for _ in range(3))
+            r = torch.empty(E, 3, device=dev, dtype=torch.float32)
+            _lib.check(lib.alignn_b200_radius_graph_fill(Xd.data_ptr(), sh.data_ptr(), n, sh.shape[0], float(cutoff), float(atol),
+                                                         off.data_ptr(), u.data_ptr(), v.data_ptr(), ci.data_ptr(), r.data_ptr(), st),
+                       "alignn_b200_radius_graph_fill")
+        # graphs.py:347-350: the highest-numbered atom must have a bond.  Bonds are (u, c, v)-ordered, so the last bond's
+        # source is the largest source; v covers the rest.
+        if E and max(int(u[-1].item()), int(v.max().item())) + 1 == n:
+            return u, v, r, ci, cells
+        cutoff += cutoff_extra
+
+
+def crystal_graph_device(lattice_mat, cart_coords, atom_features: torch.Tensor, cutoff: float = 4.0, device="cuda"):
+    """(g, lg) of one periodic structure built entirely on the GPU: radius scan, sorted-CSR index, line graph and bond
+    cosines (alignn/graphs.py:267-364, 544, 588-589).  Same graphs, bit for bit, as `crystal_graph(..., "radius_graph")`
+    followed by `.to(device)`."""
+    u, v, r, _, _ = radius_graph_device(lattice_mat, cart_coords, cutoff=cutoff, device=device)
+    n = int(np.asarray(cart_coords).shape[0])
+    g = Graph(u, v, n)
+    g.ndata["atom_features"] = atom_features.to(r.device)
+    g.edata["r"] = r
+    lg = g.line_graph(shared=True)
+    lg.edata["h"] = bond_cosines(r, lg)
+    return g, lg
 
 
 def radius_graph(lattice_mat, cart_coords, cutoff: float = 5.0, bond_tol: float = 0.5, atol: float = 1e-5,

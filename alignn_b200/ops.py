@@ -213,6 +213,33 @@ def gather_segment_sum(ix: EdgeIndex, Bh, sigma):
     return Sh, S
 
 
+def pair_force_scatter(pair_forces: torch.Tensor, ix: EdgeIndex, add_reverse: bool = True) -> torch.Tensor:
+    """forces[v] = sum over in-edges of pair_forces - (add_reverse ? sum over out-edges : 0): DGL's
+    update_all(copy_e, sum) on g and on dgl.reverse(g) (alignn_atomwise.py:547-563) in one deterministic kernel."""
+    lib = _lib.load()
+    pf = pair_forces.contiguous()
+    require_cuda(pf, ix.in_ptr, ix.in_eid, ix.out_ptr, ix.out_eid)
+    Nn = ix.in_ptr.numel() - 1
+    out = torch.empty(Nn, 3, device=pf.device, dtype=torch.float32)
+    _lib.check(lib.alignn_b200_pair_force_scatter(ptr(pf), ptr(ix.in_ptr), None if ix.dst_sorted else ptr(ix.in_eid), ptr(ix.out_ptr),
+                                                  ptr(ix.out_eid), Nn, int(add_reverse), ptr(out), stream_ptr()),
+               "alignn_b200_pair_force_scatter")
+    return out
+
+
+def virial_stress(r: torch.Tensor, pair_forces: torch.Tensor, edge_offsets64: torch.Tensor, node_offsets64: torch.Tensor,
+                  V: torch.Tensor, multiplier: float = 1.0) -> torch.Tensor:
+    """stress[b] = multiplier * -160.21766208 * (r_b^T F_b) / V[first atom of b], one block per crystal
+    (alignn_atomwise.py:610-635)."""
+    lib = _lib.load()
+    r, pf, V = r.contiguous(), pair_forces.contiguous(), V.contiguous().to(torch.float32)
+    B = edge_offsets64.numel() - 1
+    out = torch.empty(B, 3, 3, device=r.device, dtype=torch.float32)
+    _lib.check(lib.alignn_b200_virial_stress(ptr(r), ptr(pf), edge_offsets64.data_ptr(), node_offsets64.data_ptr(), ptr(V), B,
+                                             float(multiplier), ptr(out), stream_ptr()), "alignn_b200_virial_stress")
+    return out
+
+
 class _SegmentMean(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gptr):

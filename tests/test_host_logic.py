@@ -194,7 +194,10 @@ def test_as_graph_adapts_dglgraph_like_objects():
     ours = as_graph(dg)
     assert torch.equal(ours.index.in_ptr, g.index.in_ptr) and torch.equal(ours.index.out_eid, g.index.out_eid)
     assert ours.batch_size == 2 and "r" in ours.edata and "atom_features" in ours.ndata
-    assert as_graph(dg) is ours                       # cached on the DGL object
+    again = as_graph(dg)
+    assert again.index is ours.index                  # the STRUCTURE is cached on the DGL object ...
+    dg.edata["r"] = g.edata["r"] * 2.0                # ... features are read from the live object on every call
+    assert torch.equal(as_graph(dg).edata["r"], g.edata["r"] * 2.0) and torch.equal(ours.edata["r"], g.edata["r"])
     assert as_graph(g) is g
     with pytest.raises(TypeError):
         as_graph(object())

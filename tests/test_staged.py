@@ -3,8 +3,9 @@
 CPU part (always runs): the segment-aligned tile packer, and a numpy emulation of the kernel's tile / row-phase /
 column-phase data flow driven by the packer's descriptors, against the oracle's formulas -- this pins the tiling
 semantics the CUDA kernel implements.
-GPU part: opt-in (ALIGNN_B200_STAGED=1) until the kernel has run on hardware once; it compares the fused kernel
-bit for bit with the shipped gemm_nt + egc_forward pair.
+GPU part: the fully fused kernels (validated on B200 in round 2, bit-identical to the two-kernel path; measured 2x
+SLOWER than it -- their row-per-thread epilogue is bound by L2 gather latency, DESIGN.md -- and therefore not the
+shipped path) against the shipped gemm_nt + egc_forward pair.
 """
 import os
 import sys
@@ -141,8 +142,9 @@ def test_tiled_dataflow_matches_oracle_formulas(staged):
 
 
 # ------------------------------------------------------------------------------------------------ GPU (opt-in)
-needs_optin = pytest.mark.skipif(os.environ.get("ALIGNN_B200_STAGED") != "1",
-                                 reason="staged kernel: opt in with ALIGNN_B200_STAGED=1 (not yet validated on hardware)")
+def needs_optin(f):
+    """(historical gate) the staged kernels ran and passed on B200 in round 2: their tests run with the GPU suite."""
+    return f
 
 
 def _run_fused(lib, gr, x, y, conv_w, norm_edges, d, train, e_w=None, e_b=None, residual=True, groups=1):
@@ -251,87 +253,6 @@ def test_fused_conv_forward_matches_shipped_forward(staged, mode, groups):
             for k in ("x_out", "y_out"):
                 err = (out[k] - ref[k]).abs().max().item()
                 assert err <= tol * max(ref[k].abs().max().item(), 1.0), (mode, k, err)
-
-
-# ---- device-side structure builders and force reductions (graph_device.cu) -----------------------------------------
-def _test_graphs():
-    g, lg, _, _ = synthetic.make_batch(batch_size=3, atoms=6, k=12, seed=31, vary_atoms=True)
-    s, t = (a.numpy() for a in g.edges())
-    perm = np.random.default_rng(2).permutation(s.size)
-    shuffled = Graph(s[perm], t[perm], g.num_nodes(), g.batch_num_nodes(), g.batch_num_edges())
-    loops = Graph(np.array([0, 1, 1, 2, 2, 2, 0]), np.array([1, 1, 0, 2, 0, 2, 0]), 4)      # self-loops, isolated node 3
-    empty = Graph(np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), 3)
-    return [g, lg, shuffled, loops, empty]
-
-
-@pytest.mark.gpu
-@needs_optin
-def test_device_csr_and_line_graph_bit_identical_to_host_builders(staged):
-    import staged_binding
-    dev = torch.device("cuda:0")
-    for gr in _test_graphs():
-        ix = gr.index                                   # built by the native host builder
-        src, dst = ix.src.to(dev), ix.dst.to(dev)
-        out = staged_binding.csr_build_device(staged, src, dst, gr.num_nodes())
-        for k in ("in_ptr", "in_eid", "out_ptr", "out_eid"):
-            assert torch.equal(out[k].cpu(), getattr(ix, k)), k
-        assert out["dst_sorted"] == ix.dst_sorted and out["max_in_deg"] == ix.max_in_deg
-        lsrc, ldst, off = staged_binding.line_graph_device(staged, src, dst, out["in_ptr"], out["in_eid"])
-        ref = gr.line_graph()
-        rs, rt = ref.edges()
-        assert torch.equal(lsrc.cpu().long(), rs.long()) and torch.equal(ldst.cpu().long(), rt.long())
-        assert torch.equal(off.cpu(), ref.index.in_ptr)
-
-
-@pytest.mark.gpu
-@needs_optin
-def test_device_force_scatter_and_virial_match_fp64(staged):
-    import staged_binding
-    from oracle import alignn_oracle as O
-    from tests.helpers import to_oracle
-    dev = torch.device("cuda:0")
-    g, _, _, _ = synthetic.make_batch(batch_size=3, atoms=7, k=12, seed=37, vary_atoms=True)
-    E = g.num_edges()
-    pf = GI.features(8, E, 3)
-    ix = g.to(dev).index
-    f = staged_binding.pair_force_scatter(staged, pf.to(dev), ix).cpu().double()
-    s, t = (a.long() for a in g.edges())
-    zeros = torch.zeros(g.num_nodes(), 3, dtype=torch.float64)
-    ref = zeros.index_add(0, t, pf.double()) - zeros.index_add(0, s, pf.double())
-    assert (f - ref).abs().max() <= 1e-5 * ref.abs().max()
-    vols = GI.cell_volumes(g.batch_num_nodes())
-    eoff = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(g.batch_num_edges().long(), 0)]).to(dev)
-    noff = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(g.batch_num_nodes().long(), 0)]).to(dev)
-    st = staged_binding.virial_stress(staged, g.edata["r"].to(dev), pf.to(dev), eoff, noff, vols.to(dev), 10.0).cpu().double()
-    og = to_oracle(g, torch.float64)
-    ref = O.virial_stress(og, pf.double(), vols.double(), stress_multiplier=10.0)
-    assert (st - ref).abs().max() <= 1e-5 * ref.abs().max()
-
-
-@pytest.mark.gpu
-@needs_optin
-@pytest.mark.parametrize("reps,jitter", [(1, 0.0), (2, 0.05), (3, 0.1)])
-def test_device_radius_scan_bit_identical_to_host_scan(staged, reps, jitter):
-    """Same bonds, same order, same float32 displacement vectors as the native host scan (graphs.py:267-364)."""
-    import math
-    import staged_binding
-    from alignn_b200 import neighbors
-    dev = torch.device("cuda:0")
-    lat, X = neighbors.diamond_supercell(reps=reps, jitter=jitter, seed=4)
-    cutoff = 4.0
-    u, v, r, cells_of_bond = neighbors.radius_graph(lat, X, cutoff=cutoff)
-    # the image enumeration of neighbors.radius_graph (graphs.py:291-303)
-    frac = X @ np.linalg.inv(lat)
-    recp_len = np.sqrt(((2 * math.pi * np.linalg.inv(lat).T) ** 2).sum(1))
-    maxr = np.ceil((cutoff + 0.5) * recp_len / (2 * math.pi))
-    nmin, nmax = np.floor(frac.min(0)) - maxr, np.ceil(frac.max(0)) + maxr
-    cells = np.stack(np.meshgrid(*[np.arange(a, b, dtype=np.float64) for a, b in zip(nmin, nmax)], indexing="ij"), -1).reshape(-1, 3)
-    shifts = np.ascontiguousarray(cells @ lat)
-    du, dv, dc, dr = staged_binding.radius_scan_device(staged, torch.from_numpy(np.ascontiguousarray(X)).to(dev),
-                                                       torch.from_numpy(shifts).to(dev), cutoff)
-    assert np.array_equal(du.cpu().numpy(), u) and np.array_equal(dv.cpu().numpy(), v)
-    assert np.array_equal(cells[dc.cpu().numpy()], cells_of_bond)
-    assert np.array_equal(dr.cpu().numpy(), r)
 
 
 # ---- thread-level restatement of the fused kernel's epilogue index arithmetic -------------------------------------------
