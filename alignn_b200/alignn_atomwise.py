@@ -224,7 +224,7 @@ class ALIGNNAtomWise(nn.Module):
             atomwise_pred = self.fc_atomwise(x)
         forces = torch.empty(1)
         stress = torch.empty(1)
-        natoms = g.batch_num_nodes().to(out.device).to(out.dtype)
+        natoms = g.batch_num_nodes_on_device().to(out.dtype)
         en_out = out * natoms if c.energy_mult_natoms else out          # (:495-497)
         if c.use_penalty:                                               # (:498-510) zero for bonds >= threshold
             pen = torch.where(bondlength < c.penalty_threshold, c.penalty_factor * (c.penalty_threshold - bondlength),

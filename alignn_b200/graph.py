@@ -284,6 +284,14 @@ class Graph:
             lg.ndata.update(self.edata)
         return lg
 
+    def batch_num_nodes_on_device(self) -> torch.Tensor:
+        """batch_num_nodes as an int64 tensor on this graph's device (cached: no host copy inside a CUDA-graph capture)."""
+        t = getattr(self, "_bnn_dev", None)
+        if t is None or t.device != self.device:
+            t = self._bnn.to(self.device)
+            self._bnn_dev = t
+        return t
+
     def edge_graph_offsets64(self) -> torch.Tensor:
         """int64 [B+1] prefix of batch_num_edges on this graph's device (per-crystal edge ranges, virial stress)."""
         t = getattr(self, "_eoff64", None)
