@@ -30,6 +30,10 @@ GATE_EPS = 1e-6   # alignn.py:109
 # True: pass 1 = TMA-fed gather GEMM writes m and its batch statistics, pass 2 = segment reductions + edge tail.
 # False: the round-1 composition (plain GEMM writes G, the edge kernel forms m); kept for A/B runs and bit-identity tests.
 USE_GATHER_GEMM = os.environ.get("ALIGNN_B200_GATHER_GEMM", "1") != "0"
+# "1": independent kernels of a conv backward on parallel streams (see _Fork).  Measured on B200 (batch 64): 9.74 ms per
+# step forked vs 9.62 ms serial -- every one of these kernels already fills the SMs (or is a cooperative launch), so the
+# default is serial; the switch stays for small-graph workloads.
+USE_SIDE_STREAMS = os.environ.get("ALIGNN_B200_SIDE_STREAMS", "0") != "0"
 
 
 class second_order:
@@ -68,6 +72,42 @@ def _torch_ops_forward(mod, ix, x, y, need_edge_out: bool):
         yn = F.silu(mod.bn_edges(m))            # (BatchNorm: evaluated even when dead, for the running statistics)
         y_out = (y + yn if mod.residual else yn) if need_edge_out else None
     return x_out, y_out
+
+
+class _Fork:
+    """Fork / join of up to three side streams inside one autograd node, so that the independent kernels of a conv's
+    backward (node-side and edge-side reductions; the two data-gradient GEMMs and the two weight-gradient kernels) can
+    overlap: on the atom graph each of them keeps only a fraction of the SMs busy and is bound by its own pipeline
+    latency.  Results are joined on the calling stream before they are used or freed; the same pattern is legal inside
+    a CUDA-graph capture (parallel branches).  Memory: tensors allocated on a side stream are consumed on the main
+    stream after the join and the side stream re-synchronises with the main stream at the next fork, so the caching
+    allocator never hands a block to a kernel that can run before its previous reader."""
+    _pool = {}
+
+    def __init__(self, device, enabled=True):
+        self.enabled = enabled and USE_SIDE_STREAMS
+        self.main = torch.cuda.current_stream(device)
+        if self.enabled:
+            key = (device.index, self.main.cuda_stream)
+            if key not in _Fork._pool:
+                _Fork._pool[key] = [torch.cuda.Stream(device) for _ in range(3)]
+            self.side = _Fork._pool[key]
+            ev = torch.cuda.Event()
+            ev.record(self.main)
+            for s in self.side:
+                s.wait_event(ev)
+
+    def on(self, i, fn):
+        """Run `fn` on side stream i (0..2); on the calling stream when forking is disabled."""
+        if not self.enabled:
+            return fn()
+        with torch.cuda.stream(self.side[i]):
+            return fn()
+
+    def join(self):
+        if self.enabled:
+            for s in self.side:
+                self.main.wait_stream(s)
 
 
 class _Cfg:
@@ -211,22 +251,28 @@ class _EdgeGatedConvFn(torch.autograd.Function):
                 sc, sh, mu, rs = cfg.e_aux
                 e = dict(w=sc, b=sh, mean=mu, rstd=rs)
             if cfg.norm_nodes == NORM_STATS:
-                n["c1"], n["c2"] = ops.bn_backward_reduce(XP, gx_out, n["w"], n["b"], n["mean"], n["rstd"])
+                fk = _Fork(x.device)
+                cn = fk.on(0, lambda: ops.bn_backward_reduce(XP, gx_out, n["w"], n["b"], n["mean"], n["rstd"]))
                 if gy_out is not None:
                     e["c1"], e["c2"] = ops.bn_backward_reduce(M, gy_out, e["w"], e["b"], e["mean"], e["rstd"])
+                fk.join()
+                n["c1"], n["c2"] = cn
         GM, GP, vd, vs = ops.egc_backward(cfg.index, P, M, XP, S, H, gx_out, gy_out, n, e,
                                           norm_nodes=cfg.norm_nodes, norm_edges=cfg.norm_edges,
                                           gate_eps=GATE_EPS, ln_eps=cfg.ln_eps)
-        # GEMM halves of the backward on the tensor cores: data gradients (gemm_tc.cu, transposed weight
-        # images, residual added in the epilogue) and weight gradients (wgrad_tc.cu, split-K over rows)
+        # GEMM halves of the backward on the tensor cores: data gradients (gemm_fused_tc.cu, transposed weight images,
+        # residual added in the epilogue) and weight gradients (wgrad_tc.cu, split-K over rows); four independent
+        # kernels, forked over side streams
         need = ctx.needs_input_grad
         gx = gy = None
+        fk = _Fork(x.device)
         if need[1]:
-            gx = ops.gemm_gather(GP, img_catT, None, add0=gx_out if cfg.residual else None)
+            gx = fk.on(0, lambda: ops.gemm_gather(GP, img_catT, None, add0=gx_out if cfg.residual else None))
+        gWcat = fk.on(1, lambda: ops.wgrad(GP, x, groups=4))      # [4d, d] rows: src_gate | dst_update | dst_gate | src_update
+        gW_eg = fk.on(2, lambda: ops.wgrad(GM, y, groups=1))
         if need[2]:
             gy = ops.gemm_gather(GM, img_egT, None, add0=gy_out if (gy_out is not None and cfg.residual) else None)
-        gWcat = ops.wgrad(GP, x, groups=4)      # [4d, d] rows: src_gate | dst_update | dst_gate | src_update
-        gW_eg = ops.wgrad(GM, y, groups=1)
+        fk.join()
         gW_sg, gW_du, gW_dg, gW_su = gWcat[0:d], gWcat[d:2 * d], gWcat[2 * d:3 * d], gWcat[3 * d:4 * d]
         gb_sg, gb_du = vs[0], vs[1]
         gb_su, gb_dg = vd[4], vd[5]
