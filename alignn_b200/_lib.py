@@ -66,6 +66,7 @@ class GemmGatherArgs(C.Structure):
         ("add1", _fp), ("ld1", C.c_int64), ("idx1", _fp),
         ("C", _fp), ("ldc", C.c_int64),
         ("stats", _fp),
+        ("bn_scale", _fp), ("bn_shift", _fp), ("bn_mean", _fp),
         ("stream", _fp),
     ]
 

@@ -113,7 +113,7 @@ class _Fork:
 class _Cfg:
     """Per-call, non-tensor configuration of the fused stage."""
     __slots__ = ("index", "norm_nodes", "norm_edges", "residual", "need_edge_out", "ln_eps",
-                 "bn_nodes", "bn_edges", "n_aux", "e_aux", "images", "legacy_w")
+                 "bn_nodes", "bn_edges", "n_aux", "e_aux", "images", "legacy_w", "up_link", "e_link")
 
 
 def _bn_eval_vectors(bn: nn.BatchNorm1d):
@@ -184,6 +184,8 @@ class _EdgeGatedConvFn(torch.autograd.Function):
                                   residual=cfg.residual, save=needs_grad, need_edge_out=cfg.need_edge_out and Ne > 0,
                                   gate_eps=GATE_EPS, ln_eps=cfg.ln_eps, gate_is_m=True)
             x_out, y_out = out["x_out"], out["y_out"]
+            if stats and needs_grad and y_out is not None and ops.USE_BN_LINKS:
+                cfg.e_link = ops.BNLink(M, e_aux[0], e_aux[1], e_aux[2], e_aux[3], Ne)
             if stats:
                 track_n = bnn.track_running_stats and bnn.running_mean is not None
                 n_aux = ops.bn_finalize(out["partials"], 1, Nn, nw, nb, bnn.eps, _momentum(bnn),
@@ -254,7 +256,9 @@ class _EdgeGatedConvFn(torch.autograd.Function):
                 fk = _Fork(x.device)
                 cn = fk.on(0, lambda: ops.bn_backward_reduce(XP, gx_out, n["w"], n["b"], n["mean"], n["rstd"]))
                 if gy_out is not None:
-                    e["c1"], e["c2"] = ops.bn_backward_reduce(M, gy_out, e["w"], e["b"], e["mean"], e["rstd"])
+                    got = cfg.e_link.take(gy_out) if cfg.e_link is not None else None   # sums from the consumer's GEMM epilogue
+                    e["c1"], e["c2"] = got if got is not None else \
+                        ops.bn_backward_reduce(M, gy_out, e["w"], e["b"], e["mean"], e["rstd"])
                 fk.join()
                 n["c1"], n["c2"] = cn
         GM, GP, vd, vs = ops.egc_backward(cfg.index, P, M, XP, S, H, gx_out, gy_out, n, e,
@@ -271,7 +275,15 @@ class _EdgeGatedConvFn(torch.autograd.Function):
         gWcat = fk.on(1, lambda: ops.wgrad(GP, x, groups=4))      # [4d, d] rows: src_gate | dst_update | dst_gate | src_update
         gW_eg = fk.on(2, lambda: ops.wgrad(GM, y, groups=1))
         if need[2]:
-            gy = ops.gemm_gather(GM, img_egT, None, add0=gy_out if (gy_out is not None and cfg.residual) else None)
+            res = gy_out if (gy_out is not None and cfg.residual) else None
+            up = cfg.up_link
+            if up is not None and up.usable_for(y):
+                # the gradient leaving here feeds a train-mode BatchNorm + SiLU upstream: its two reductions ride on the
+                # epilogue of this GEMM (ops.BNLink)
+                gy, up.partials = ops.gemm_gather(GM, img_egT, None, add0=res, bn_aux=(up.rows, up.scale, up.shift, up.mean))
+                up.grad_ptr = gy.data_ptr()
+            else:
+                gy = ops.gemm_gather(GM, img_egT, None, add0=res)
         fk.join()
         gW_sg, gW_du, gW_dg, gW_su = gWcat[0:d], gWcat[d:2 * d], gWcat[2 * d:3 * d], gWcat[3 * d:4 * d]
         gb_sg, gb_du = vs[0], vs[1]
@@ -358,6 +370,8 @@ class EdgeGatedGraphConvBase(nn.Module):
         cfg.n_aux = cfg.e_aux = None
         cfg.legacy_w = None
         cfg.images = None
+        cfg.e_link = None
+        cfg.up_link = getattr(edge_feats, "_alignn_b200_bn_link", None) if (USE_GATHER_GEMM and ops.USE_BN_LINKS) else None
         if USE_GATHER_GEMM:
             cfg.images = self.image_table()
             cfg.images.refresh()          # no launch if the model-level table already refreshed this step
@@ -370,6 +384,8 @@ class EdgeGatedGraphConvBase(nn.Module):
             cfg.ln_eps = 1e-5
         with torch.cuda.device(node_feats.device):     # kernels launch on the tensors' device, whatever the current one is
             x, y = self._run_kernels(cfg, node_feats, edge_feats)
+        if _need_edge_out and cfg.e_link is not None:
+            y._alignn_b200_bn_link = cfg.e_link         # see ops.BNLink
         return x, (y if _need_edge_out else None)
 
     def _run_kernels(self, cfg, node_feats, edge_feats):

@@ -72,6 +72,9 @@ struct Params {
   const float* add1; int64_t ld1; const int32_t* idx1;
   float* C; int64_t ldc;
   float* stats;                                          // [gridDim.x][2][N] or NULL (requires N == BN)
+  const float* bn_scale; const float* bn_shift; const float* bn_mean;   // != NULL: add1 rows are NOT added; they are the
+                                                         // pre-norm rows m of the BatchNorm+SiLU that produced this GEMM's
+                                                         // input gradient, and stats = sum gu, sum gu (m - mean)
   long long* trace;                                      // development aid: per-role event clocks of CTA 0 ([6][512]) or NULL
 };
 
@@ -80,6 +83,10 @@ struct Params {
 
 __host__ __device__ constexpr int plane_off(int r, int k) { return (r >> 3) * (int)SBO + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2; }
 
+__device__ __forceinline__ float dsilu_(float u) {          // d/du [u * sigmoid(u)], same formula as egc_kernels.cu
+  const float sg = 1.f / (1.f + __expf(-u));
+  return sg * (1.f + u * (1.f - sg));
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(tc::smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(tc::smem_u32(bar)) : "memory");
@@ -92,7 +99,7 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, 
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 
-template <int BN>
+template <int BN, bool BNMODE>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapC, const Params p) {
   using F = Cfg<BN>;
@@ -224,6 +231,7 @@ gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     float* stat = reinterpret_cast<float*>(smem + F::OFF_STAT) + q * 2 * BN;
     const int half = ew >> 2;                                // which of the quarter's two warps: chunks half, half + 2, ...
     const bool do_stats = p.stats != nullptr;
+    constexpr bool bnmode = BNMODE;
     if (do_stats)
       for (int ch = half; ch < BN / 32; ch += 2) { stat[ch * 32 + lane] = 0.f; stat[BN + ch * 32 + lane] = 0.f; }
     const int rsub = lane >> 3;                              // row within a group of 4
@@ -278,6 +286,12 @@ gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
         if (ew == 0 && lane == 0) GEMM2_TRACE(5, tr5);
         float4 b4 = z4;
         if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + c4));
+        float4 bsc = z4, bsh = z4, bmu = z4;
+        if (bnmode) {
+          bsc = __ldg(reinterpret_cast<const float4*>(p.bn_scale + n0 + c0 + c4));
+          bsh = __ldg(reinterpret_cast<const float4*>(p.bn_shift + n0 + c0 + c4));
+          bmu = __ldg(reinterpret_cast<const float4*>(p.bn_mean + n0 + c0 + c4));
+        }
         float4 s4 = z4, q4 = z4;
         const bool more = ch + 2 < NCH;
 #pragma unroll
@@ -285,18 +299,31 @@ gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
           const int r = it * 4 + rsub;
           float4* cell = reinterpret_cast<float4*>(stg + r * 128 + (((lane & 7) ^ (r & 7)) << 4));
           float4 o = *cell;
-          o.x = (o.x + b4.x) + (a0[it].x + a1[it].x);
-          o.y = (o.y + b4.y) + (a0[it].y + a1[it].y);
-          o.z = (o.z + b4.z) + (a0[it].z + a1[it].z);
-          o.w = (o.w + b4.w) + (a0[it].w + a1[it].w);
+          const float4 mrow = a1[it];                       // (BatchNorm mode: the pre-norm row, not an addend)
+          const float4 ad1 = bnmode ? z4 : mrow;
+          o.x = (o.x + b4.x) + (a0[it].x + ad1.x);
+          o.y = (o.y + b4.y) + (a0[it].y + ad1.y);
+          o.z = (o.z + b4.z) + (a0[it].z + ad1.z);
+          o.w = (o.w + b4.w) + (a0[it].w + ad1.w);
           // this row's addends of the NEXT chunk go out now and land while the rest of this chunk is processed
           if (more) {
             if (i0[it] >= 0) a0[it] = __ldg(reinterpret_cast<const float4*>(base0 + (int64_t)i0[it] * p.ld0 + (c0 - half * 32) + 64));
             if (i1[it] >= 0) a1[it] = __ldg(reinterpret_cast<const float4*>(base1 + (int64_t)i1[it] * p.ld1 + (c0 - half * 32) + 64));
           }
           if ((rvm >> it) & 1u) {
-            s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
-            q4.x = fmaf(o.x, o.x, q4.x); q4.y = fmaf(o.y, o.y, q4.y); q4.z = fmaf(o.z, o.z, q4.z); q4.w = fmaf(o.w, o.w, q4.w);
+            if (bnmode) {
+              // gu = o * silu'(m * scale + shift);  partial sums of gu and gu * (m - mean): the two reductions of the
+              // train-mode BatchNorm backward (c1, c2) for the layer that consumes this gradient
+              float4 gu;
+              gu.x = o.x * dsilu_(fmaf(mrow.x, bsc.x, bsh.x)); gu.y = o.y * dsilu_(fmaf(mrow.y, bsc.y, bsh.y));
+              gu.z = o.z * dsilu_(fmaf(mrow.z, bsc.z, bsh.z)); gu.w = o.w * dsilu_(fmaf(mrow.w, bsc.w, bsh.w));
+              s4.x += gu.x; s4.y += gu.y; s4.z += gu.z; s4.w += gu.w;
+              q4.x = fmaf(gu.x, mrow.x - bmu.x, q4.x); q4.y = fmaf(gu.y, mrow.y - bmu.y, q4.y);
+              q4.z = fmaf(gu.z, mrow.z - bmu.z, q4.z); q4.w = fmaf(gu.w, mrow.w - bmu.w, q4.w);
+            } else {
+              s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
+              q4.x = fmaf(o.x, o.x, q4.x); q4.y = fmaf(o.y, o.y, q4.y); q4.z = fmaf(o.z, o.z, q4.z); q4.w = fmaf(o.w, o.w, q4.w);
+            }
           }
           if constexpr (kTmaStore) *cell = o;
           else if ((rvm >> it) & 1u)
@@ -424,19 +451,24 @@ static long long* g_trace = nullptr;   // set by alignn_b200_debug_gemm_trace (d
 
 inline int pick_bn(int N) { return (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : (N % 32 == 0) ? 32 : 0; }
 
-template <int BN>
-int launch(const CUtensorMap& mapA, const CUtensorMap& mapC, const Params& p, cudaStream_t st) {
+template <int BN, bool BNMODE>
+int launch2(const CUtensorMap& mapA, const CUtensorMap& mapC, const Params& p, cudaStream_t st) {
   using F = Cfg<BN>;
   static std::atomic<bool> configured{false};
   if (!configured.load(std::memory_order_acquire)) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_gather_bf16x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_gather_bf16x3_kernel<BN, BNMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
     if (e != cudaSuccess) return record_cuda_error((int)e);
     configured.store(true, std::memory_order_release);
   }
   const int total = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = total < 148 ? total : 148;
-  gemm_gather_bf16x3_kernel<BN><<<grid, THREADS, F::SMEM, st>>>(mapA, mapC, p);
+  gemm_gather_bf16x3_kernel<BN, BNMODE><<<grid, THREADS, F::SMEM, st>>>(mapA, mapC, p);
   return check_launch();
+}
+
+template <int BN>
+int launch(const CUtensorMap& mapA, const CUtensorMap& mapC, const Params& p, cudaStream_t st) {
+  return p.bn_scale ? launch2<BN, true>(mapA, mapC, p, st) : launch2<BN, false>(mapA, mapC, p, st);
 }
 
 }  // namespace gemm2
@@ -467,6 +499,7 @@ int alignn_b200_gemm_gather(const alignn_b200_gemm_gather_args* a) {
   const int bn = pick_bn(a->N);
   if (bn == 0) return ALIGNN_ERR_UNSUPPORTED_D;
   if (a->stats && a->N != bn) return ALIGNN_ERR_BAD_ARG;      // column statistics need the whole row in one tile
+  if (a->bn_scale && (!a->bn_shift || !a->bn_mean || !a->add1 || !a->stats)) return ALIGNN_ERR_BAD_ARG;
   CUtensorMap mapA, mapC;
   int rc = make_map_f32(&mapA, a->A, a->M, a->K, a->lda, BM);
   if (rc != ALIGNN_OK) return rc;
@@ -479,6 +512,7 @@ int alignn_b200_gemm_gather(const alignn_b200_gemm_gather_args* a) {
   p.add0 = a->add0; p.ld0 = a->ld0; p.idx0 = a->idx0;
   p.add1 = a->add1; p.ld1 = a->ld1; p.idx1 = a->idx1;
   p.C = a->C; p.ldc = a->ldc; p.stats = a->stats;
+  p.bn_scale = a->bn_scale; p.bn_shift = a->bn_shift; p.bn_mean = a->bn_mean;
   p.trace = g_trace;
   cudaStream_t st = (cudaStream_t)a->stream;
   switch (bn) {

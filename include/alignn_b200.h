@@ -258,6 +258,12 @@ typedef struct {
   const float* add1; int64_t ld1; const int32_t* idx1;
   float* C; int64_t ldc;
   float* stats;                                             /* [stat_rows][2][N] or NULL */
+  /* BatchNorm-backward mode (all three != NULL; needs add1 and stats): the rows add1[i1(r)] are NOT added -- they are
+   * the pre-norm rows m of the train-mode BatchNorm1d + SiLU whose output gradient this GEMM produces (C = dL/d(out)),
+   * bn_scale / bn_shift / bn_mean [N] its batch scale, shift and mean; stats then holds the partial sums of
+   * gu = C * silu'(m * scale + shift) and gu * (m - mean): the two reductions of that BatchNorm's backward
+   * (alignn_b200_bn_backward_reduce) without another pass over C and m. */
+  const float* bn_scale; const float* bn_shift; const float* bn_mean;
   alignn_stream_t stream;
 } alignn_b200_gemm_gather_args;
 
