@@ -31,6 +31,8 @@
 namespace alignn {
 namespace gemm2 {
 
+int make_map_f32(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+
 constexpr int BM = 128;
 constexpr int BK = 32;
 constexpr int NSA = 3;          // fp32 A staging ring (TMA destination); L2 prefetch one tile ahead covers the HBM latency
@@ -365,14 +367,10 @@ gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     if (kTmaStore && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // smem must outlive the last TMA stores
     if (do_stats) {
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      // one partial row per (CTA, lane quarter): [4 * gridDim.x][2][BN] (the same layout as the pair kernel)
       const float* all = reinterpret_cast<const float*>(smem + F::OFF_STAT);
-      float* out_row = p.stats + (int64_t)blockIdx.x * 2 * BN;
-      for (int i = ew * 32 + lane; i < 2 * BN; i += EPI_WARPS * 32) {
-        float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) t += all[w * 2 * BN + i];
-        out_row[i] = t;
-      }
+      float* out_rows = p.stats + (int64_t)blockIdx.x * 4 * 2 * BN;
+      for (int i = ew * 32 + lane; i < 4 * 2 * BN; i += EPI_WARPS * 32) out_rows[i] = all[i];
     }
   } else if (warp == 0 && lane == 0) {
     // ================= MMA issuer (one thread) =================
@@ -461,7 +459,9 @@ int launch2(const CUtensorMap& mapA, const CUtensorMap& mapC, const Params& p, c
     configured.store(true, std::memory_order_release);
   }
   const int total = ((p.M + BM - 1) / BM) * (p.N / BN);
-  const int grid = total < 148 ? total : 148;
+  int grid = total < 148 ? total : 148;
+  if (p.stats) grid = alignn_b200_gemm_gather_stat_rows(p.M, p.N) / 4;    // one partial row per CTA, whichever kernel runs (a CTA
+                                                                      // without tiles writes zeros)
   gemm_gather_bf16x3_kernel<BN, BNMODE><<<grid, THREADS, F::SMEM, st>>>(mapA, mapC, p);
   return check_launch();
 }
@@ -481,9 +481,13 @@ void alignn_b200_debug_gemm_trace(long long* device_buffer) { alignn::gemm2::g_t
 int alignn_b200_gemm_gather_stat_rows(int64_t M, int N) {
   const int bn = alignn::gemm2::pick_bn(N);
   if (bn == 0 || M <= 0) return 0;
-  const int64_t total = ((M + alignn::gemm2::BM - 1) / alignn::gemm2::BM) * (N / bn);
-  return (int)(total < 148 ? total : 148);
+  // CTAs of the launch (statistics need N == bn: one column tile): the same count for the one-CTA kernel and for the
+  // pair kernel (two CTAs per 256-row tile)
+  const int64_t total = 2 * ((M + 2 * alignn::gemm2::BM - 1) / (2 * alignn::gemm2::BM));
+  return 4 * (int)(total < 148 ? total : 148);       // four lane quarters per CTA, one partial row each
 }
+
+int alignn_b200_gemm_gather_try_pair(const alignn_b200_gemm_gather_args* a, int* status);   /* gemm_pair_tc.cu */
 
 int alignn_b200_gemm_gather(const alignn_b200_gemm_gather_args* a) {
   using namespace alignn::gemm2;
@@ -500,6 +504,10 @@ int alignn_b200_gemm_gather(const alignn_b200_gemm_gather_args* a) {
   if (bn == 0) return ALIGNN_ERR_UNSUPPORTED_D;
   if (a->stats && a->N != bn) return ALIGNN_ERR_BAD_ARG;      // column statistics need the whole row in one tile
   if (a->bn_scale && (!a->bn_shift || !a->bn_mean || !a->add1 || !a->stats)) return ALIGNN_ERR_BAD_ARG;
+  {
+    int st = ALIGNN_OK;
+    if (alignn_b200_gemm_gather_try_pair(a, &st)) return st;     // N = 256, K <= 256: the two-CTA kernel (gemm_pair_tc.cu)
+  }
   CUtensorMap mapA, mapC;
   int rc = make_map_f32(&mapA, a->A, a->M, a->K, a->lda, BM);
   if (rc != ALIGNN_OK) return rc;

@@ -30,6 +30,14 @@ def timeit(fn, iters=15):
     return ts[len(ts) // 2]
 
 
+def set_pair(on):
+    from alignn_b200 import _lib
+    import ctypes as C
+    f = _lib.load().alignn_b200_debug_gemm_pair
+    f.argtypes, f.restype = [C.c_int], None
+    f(int(on))
+
+
 def main():
     d = 256
     E, T = 23040, 276480
@@ -47,10 +55,18 @@ def main():
     hbm = 6385.8
     t = timeit(lambda: ops.gemm_nt(y, img, b, out=out))
     res["gemm_nt_lg"] = dict(us=round(t, 1), frac=round(4 * T * d * 2 / t / 1e3 / hbm, 3))
-    t = timeit(lambda: ops.gemm_gather(y, img, b, out=out))
-    res["gather_plain_lg"] = dict(us=round(t, 1), frac=round(4 * T * d * 2 / t / 1e3 / hbm, 3))
-    t = timeit(lambda: ops.gemm_gather(y, img, None, add0=P[:, 0:d], idx0=src, add1=P[:, 2 * d:3 * d], idx1=dst, stats=True, out=out))
-    res["gather_gate_stats_lg"] = dict(us=round(t, 1), frac=round(4 * T * d * 2 / t / 1e3 / hbm, 3))
+    for pair in (0, 1):
+        set_pair(pair)
+        tag = "pair" if pair else "1cta"
+        t = timeit(lambda: ops.gemm_gather(y, img, b, out=out))
+        res[f"gather_plain_lg_{tag}"] = dict(us=round(t, 1), frac=round(4 * T * d * 2 / t / 1e3 / hbm, 3))
+        t = timeit(lambda: ops.gemm_gather(y, img, None, add0=P[:, 0:d], idx0=src, add1=P[:, 2 * d:3 * d], idx1=dst, stats=True, out=out))
+        res[f"gather_gate_stats_lg_{tag}"] = dict(us=round(t, 1), frac=round(4 * T * d * 2 / t / 1e3 / hbm, 3))
+        t = timeit(lambda: ops.gemm_gather(y, img, None, add0=R, out=out))
+        res[f"gather_residual_lg_{tag}"] = dict(us=round(t, 1), frac=round(4 * T * d * 3 / t / 1e3 / hbm, 3))
+        yg_ = torch.randn(E, d, generator=g).to(dev)
+        t = timeit(lambda: ops.gemm_gather(yg_, img, b))
+        res[f"gather_g_{tag}"] = dict(us=round(t, 1))
     t = timeit(lambda: ops.gemm_nt(y, img, None, R, out=out))
     res["gemm_nt_residual_lg"] = dict(us=round(t, 1), frac=round(4 * T * d * 3 / t / 1e3 / hbm, 3))
     t = timeit(lambda: ops.gemm_gather(y, img, None, add0=R, out=out))
