@@ -487,7 +487,7 @@ int alignn_b200_gemm_gather_stat_rows(int64_t M, int N) {
   return 4 * (int)(total < 148 ? total : 148);       // four lane quarters per CTA, one partial row each
 }
 
-int alignn_b200_gemm_gather_try_pair(const alignn_b200_gemm_gather_args* a, int* status);   /* gemm_pair_tc.cu */
+__attribute__((visibility("hidden"))) int alignn_b200_gemm_gather_try_pair(const alignn_b200_gemm_gather_args* a, int* status);   /* gemm_pair_tc.cu */
 
 int alignn_b200_gemm_gather(const alignn_b200_gemm_gather_args* a) {
   using namespace alignn::gemm2;

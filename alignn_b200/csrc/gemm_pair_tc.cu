@@ -445,7 +445,7 @@ extern "C" {
 void alignn_b200_debug_gemm_pair(int enabled) { alignn::gemmp::g_pair_enabled.store(enabled); }   /* A/B switch, not in the public header */
 
 /* called by alignn_b200_gemm_gather (gemm_fused_tc.cu) for the shapes the pair kernel covers; returns 1 if it took the call */
-int alignn_b200_gemm_gather_try_pair(const alignn_b200_gemm_gather_args* a, int* status) {
+__attribute__((visibility("hidden"))) int alignn_b200_gemm_gather_try_pair(const alignn_b200_gemm_gather_args* a, int* status) {
   using namespace alignn::gemmp;
   if (!g_pair_enabled.load() || a->N != BN || a->K > MAX_NK * BK || a->K % BK || a->bn_scale || a->M < 2 * BM) return 0;
   CUtensorMap mapA, mapC;

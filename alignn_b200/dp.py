@@ -115,8 +115,12 @@ class FlatGradAllReducer:
         w = self.world_size
         if w == 1:
             return None
-        self.flat.div_(w)              # pre-scale, then SUM (gloo has no AVG)
-        self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+        if self.flat.is_cuda and dist.get_backend(self.group) == "nccl":
+            # NCCL averages inside the collective (in-switch reduction on NVSwitch when NVLS is up): no scaling kernel
+            self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
+        else:
+            self.flat.div_(w)          # gloo has no AVG: pre-scale, then SUM
+            self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
         return self._work
 
     def wait(self) -> None:

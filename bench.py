@@ -262,9 +262,12 @@ def run_ours(args):
                 tgt.to(dev, non_blocking=True))
 
     def barrier():
-        if world > 1:
-            dist.barrier()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group_ref[0]) if cpu_group_ref[0] is not None else dist.barrier()
+        torch.cuda.synchronize()
+
+    cpu_group_ref = [None]
 
     # everything below (warm-up, capture, every timed region) runs on ONE side stream: the autograd accumulators are
     # created on the stream that later replays them
@@ -282,6 +285,10 @@ def run_ours(args):
                 fn(i)
             e1.record()
         barrier()
+        if world > 1 and cpu_group_ref[0] is not None:
+            ms = torch.tensor([e0.elapsed_time(e1)])
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX, group=cpu_group_ref[0])
+            return ms.item()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -293,8 +300,12 @@ def run_ours(args):
         first = timed(fn, steps)
         reps = int(max(1, min(max_reps, budget_s * 1e3 / max(first, 1e-3))))
         if world > 1:
-            t = torch.tensor([reps], device=dev)
-            dist.broadcast(t, 0)
+            if cpu_group_ref[0] is not None:
+                t = torch.tensor([reps])
+                dist.broadcast(t, 0, group=cpu_group_ref[0])
+            else:
+                t = torch.tensor([reps], device=dev)
+                dist.broadcast(t, 0)
             reps = int(t.item())
         all_ms = [first] + [timed(fn, steps) for _ in range(reps - 1)]
         return statistics.median(all_ms), all_ms
@@ -317,6 +328,14 @@ def run_ours(args):
     # all-reduce -> replay(optimizer).
     graphs_res, graphs_e2e, graph_opt, launches_per_step = [], [], None, None
 
+    # ALIGNN_B200_NCCL_IN_GRAPH=1: capture the all-reduce and the optimizer into the same graph as forward + backward
+    # (one replay per step).  Round 1 reported a hang: the capture and the replays are fine (tools/nccl_in_graph_probe.py,
+    # capture_error_mode="thread_local" keeps the process-group watchdog out of the capture); what hangs on this stack is
+    # an eager NCCL barrier AFTER captured collectives were replayed, so the rank barrier of the timed regions is a
+    # gloo (CPU) barrier in this mode.  Opt-in until it has run at 8 GPUs.
+    nccl_in_graph = use_graph and world > 1 and os.environ.get("ALIGNN_B200_NCCL_IN_GRAPH", "0") == "1"
+    cpu_group_ref[0] = dist.new_group(backend="gloo") if nccl_in_graph else None
+
     def fwd_bwd(batch):
         g, lg, lat, tgt = batch
         reducer.zero_grad()
@@ -324,6 +343,9 @@ def run_ours(args):
         loss = (out - tgt).abs().mean()
         loss.backward()
         reducer.gather()                                      # gradients -> flat buffer (one multi-tensor copy)
+        if nccl_in_graph:
+            reducer.reduce_flat()
+            opt.step()
         return loss
 
     if use_graph:
@@ -331,26 +353,28 @@ def run_ours(args):
         for b in range(nb):
             gr = torch.cuda.CUDAGraph()
             l0 = _lib.launch_count()
-            with torch.cuda.graph(gr, pool=pool, stream=work):
+            with torch.cuda.graph(gr, pool=pool, stream=work, capture_error_mode="thread_local" if nccl_in_graph else "global"):
                 loss_b = fwd_bwd(resident[b])
             launches_per_step = _lib.launch_count() - l0
             pool = pool or gr.pool()
             graphs_res.append((gr, loss_b))
         for b in range(nb):
             gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr, pool=pool, stream=work):
+            with torch.cuda.graph(gr, pool=pool, stream=work, capture_error_mode="thread_local" if nccl_in_graph else "global"):
                 loss_b = fwd_bwd(h2d(b))
             graphs_e2e.append((gr, loss_b))
-        graph_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph_opt, pool=pool, stream=work):
-            opt.step()
+        if not nccl_in_graph:
+            graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_opt, pool=pool, stream=work):
+                opt.step()
         barrier()
 
     def run_resident(i):
         if use_graph:
             graphs_res[i % nb][0].replay()
-            reducer.reduce_flat()
-            graph_opt.replay()
+            if not nccl_in_graph:
+                reducer.reduce_flat()
+                graph_opt.replay()
         else:
             step(resident[i % nb])
 
@@ -358,8 +382,9 @@ def run_ours(args):
         if use_graph:
             gr, loss_b = graphs_e2e[i % nb]
             gr.replay()
-            reducer.reduce_flat()
-            graph_opt.replay()
+            if not nccl_in_graph:
+                reducer.reduce_flat()
+                graph_opt.replay()
             return loss_b.item()                              # D2H + sync, as train.py:300-305 does
         return step(h2d(i)).item()
 
@@ -392,12 +417,16 @@ def run_ours(args):
     ksum = ops.TIMER.summary()
     ops.TIMER = None
 
-    lt = torch.tensor([launches], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(lt)
+    if world > 1 and cpu_group_ref[0] is not None:
+        lt = torch.tensor([launches], dtype=torch.float64)
+        dist.all_reduce(lt, group=cpu_group_ref[0])
+    else:
+        lt = torch.tensor([launches], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(lt)
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            _finish(nccl_in_graph)
         return
 
     graphs_per_step = args.batch * world
@@ -438,7 +467,7 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "model": "ALIGNN 4+4 d=256 (" + args.norm + ", train mode)",
                    "global_batch": graphs_per_step, "per_gpu_batch": args.batch, "N": N, "E": E, "T": T,
                    "parallelism": f"dp{world}", "optimizer": "AdamW(fused, one flat parameter)", "loss": "L1",
-                   "cuda_graph": use_graph, "eager_ms_per_step": ms_eager / args.steps,
+                   "cuda_graph": use_graph, "allreduce_in_graph": bool(nccl_in_graph), "eager_ms_per_step": ms_eager / args.steps,
                    "timing": f"median of {len(reps_res)} repetitions of exactly {args.steps} steps (each: events on the launching "
                              f"stream, barrier + synchronize on both sides, max over ranks)",
                    "repetition_ms": [round(m, 3) for m in reps_res],
@@ -462,7 +491,16 @@ def run_ours(args):
                                           f"{threads} threads of the box's {os.cpu_count()} cores"}
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        _finish(nccl_in_graph)
+
+
+def _finish(hard_exit):
+    """Tear the process group down; after replayed in-graph collectives the NCCL teardown hangs on this stack, so that
+    mode leaves through os._exit once everything is printed."""
+    sys.stdout.flush()
+    if hard_exit:
+        os._exit(0)
+    dist.destroy_process_group()
 
 
 def main():

@@ -367,6 +367,13 @@ int alignn_b200_segment_mean(const float* x, const int32_t* graph_ptr /*[B+1]*/,
 int alignn_b200_segment_mean_backward(const float* g_out /*[B,d]*/, const int32_t* graph_ptr, int64_t B, int d,
                                       float* gx /*[N,d]*/, alignn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Development aids (A/B switches and tracing used by tools/; not needed by a caller of the path).
+ * ---------------------------------------------------------------------------------------- */
+void alignn_b200_debug_gemm_flags(int flags);               /* knock-out bits of the round-1 register-fed GEMM (gemm_nt) */
+void alignn_b200_debug_gemm_pair(int enabled);              /* route N = 256, K <= 256 gemm_gather calls to the two-CTA kernel */
+void alignn_b200_debug_gemm_trace(long long* device_buffer); /* per-role SM-clock timeline of CTA 0 of gemm_gather ([6][512]) */
+
 #ifdef __cplusplus
 }
 #endif

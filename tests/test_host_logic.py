@@ -109,6 +109,10 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name)
+    # and the reverse: the shared object exports no alignn_b200_* symbol the header does not declare
+    nm = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    exported = {ln.split()[-1] for ln in nm.splitlines() if ln.split() and ln.split()[-1].startswith("alignn_b200_")}
+    assert exported == declared, exported ^ declared
     assert lib.alignn_b200_version() == 100
     assert lib.alignn_b200_strerror(-2).decode().startswith("unsupported feature width")
     assert lib.alignn_b200_egc_partial_rows(1920, 256) == 240
