@@ -1,4 +1,7 @@
-/* STAGED WORK -- not part of libalignn_b200.so, not declared in include/alignn_b200.h.
+/* EXPERIMENTAL -- not part of libalignn_b200.so, not declared in include/alignn_b200.h.
+ * Status (round 2): ran on B200, bit-identical to the shipped two-kernel path (tests/test_staged.py), measured ~2x
+ * SLOWER than it (profiles/r02_staged_fused_ab.jsonl): the row-per-thread epilogue is bound by L2 gather latency.
+ * The shipped forward is the two-pass composition of DESIGN.md section 2.  Original header follows.
  *
  * One-kernel forward of the edge side of EdgeGatedGraphConv (alignn/models/alignn.py:100-109,123,127):
  * the edge-gate Linear (`self.edge_gate(edge_feats)`, :101) runs on tcgen05 into TMEM and the gate / segment-sum

@@ -111,7 +111,7 @@ def cpu_calibrate(args, graphs):
         dt = time.perf_counter() - t0
         if best is None or dt < best[1]:
             best = (th, dt)
-    return best[0]
+    return best
 
 
 def cpu_oracle_run(args, graphs, steps, warmup, threads):
@@ -133,14 +133,20 @@ def run_reference(args):
     if rank != 0:
         return
     graphs = args.cpu_sample_graphs if args.cpu_sample_graphs > 0 else args.batch     # the full 64-graph batch by default
-    threads = cpu_calibrate(args, graphs)
-    gps, ms = cpu_oracle_run(args, graphs, args.steps, max(1, min(args.warmup, 3)), threads)
+    threads, dt = cpu_calibrate(args, graphs)
+    warm = max(1, min(args.warmup, 3))
+    if args.cpu_sample_graphs <= 0 and (args.steps + warm) * dt > 150.0:
+        # keep the whole run within a few minutes: a bounded sample of the batch per step (time per graph is flat in the
+        # batch size for this path: block-diagonal graphs)
+        graphs = int(max(8, min(args.batch, args.batch * 150.0 / ((args.steps + warm) * dt))))
+    gps, ms = cpu_oracle_run(args, graphs, args.steps, warm, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": gps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "model": "ALIGNN 4+4 d=256 (" + args.norm + ", train mode)",
-                   "global_batch": graphs, "per_gpu_batch": graphs, "parallelism": "cpu", "optimizer": "AdamW", "loss": "L1",
+                   "global_batch": graphs, "per_gpu_batch": graphs, "parallelism": "dp1", "optimizer": "AdamW", "loss": "L1",
+                   "device": "host cores (reference arm)",
                    "sample": f"{graphs} graphs per step" + ("" if graphs == args.batch else " (bounded CPU sample of the 64-graph batch)")},
         "cpu_baseline": {"value": gps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps x {graphs} graphs, torch-CPU restatement of the reference DGL path "
@@ -466,7 +472,8 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "model": "ALIGNN 4+4 d=256 (" + args.norm + ", train mode)",
                    "global_batch": graphs_per_step, "per_gpu_batch": args.batch, "N": N, "E": E, "T": T,
-                   "parallelism": f"dp{world}", "optimizer": "AdamW(fused, one flat parameter)", "loss": "L1",
+                   "parallelism": f"dp{world}", "optimizer": "AdamW", "loss": "L1",
+                   "device": "B200", "optimizer_impl": "fused, one flat parameter (alignn_b200.dp.FlatAdamW)",
                    "cuda_graph": use_graph, "allreduce_in_graph": bool(nccl_in_graph), "eager_ms_per_step": ms_eager / args.steps,
                    "timing": f"median of {len(reps_res)} repetitions of exactly {args.steps} steps (each: events on the launching "
                              f"stream, barrier + synchronize on both sides, max over ranks)",

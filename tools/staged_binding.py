@@ -1,5 +1,7 @@
-"""ctypes binding of the staged library (alignn_b200/csrc/staged/egc_fused.h), shared by tests/test_staged.py and
-tools/bench_fused.py.  Not part of the product: the shipped binding is alignn_b200/_lib.py."""
+"""ctypes binding of the experimental library (alignn_b200/csrc/staged/egc_fused.h: the fully fused one-kernel conv
+forward / backward), shared by tests/test_staged.py and tools/bench_fused*.py.  Not part of the product: the shipped
+binding is alignn_b200/_lib.py.  (The device-side structure builders that used to live here are shipped now:
+alignn_b200/csrc/graph_device.cu, include/alignn_b200.h.)"""
 import ctypes as C
 import os
 
@@ -111,121 +113,6 @@ def conv_forward_like(lib, ix, tiles_d, n_tiles, x, y, img, b_eg, P, n_w, n_b, e
             raise RuntimeError(f"alignn_b200_ln_silu_residual -> {rc}")
         out["x_out"] = xo
     return out
-
-
-# ---- device-side structure builders / force reductions (csrc/staged/graph_device.h) ------------------------------
-def _sig(lib):
-    vp, i64, i32, f32, sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
-    lib.alignn_b200_csr_build_workspace_bytes.restype = sz
-    lib.alignn_b200_csr_build_workspace_bytes.argtypes = [i64, i64]
-    lib.alignn_b200_csr_build.restype = i32
-    lib.alignn_b200_csr_build.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, sz, vp]
-    lib.alignn_b200_line_graph_workspace_bytes.restype = sz
-    lib.alignn_b200_line_graph_workspace_bytes.argtypes = [i64]
-    lib.alignn_b200_line_graph_offsets.restype = i32
-    lib.alignn_b200_line_graph_offsets.argtypes = [vp, vp, vp, i64, vp, vp, sz, vp]
-    lib.alignn_b200_line_graph_fill.restype = i32
-    lib.alignn_b200_line_graph_fill.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp]
-    lib.alignn_b200_radius_graph_workspace_bytes.restype = sz
-    lib.alignn_b200_radius_graph_workspace_bytes.argtypes = [i64]
-    lib.alignn_b200_radius_graph_offsets.restype = i32
-    lib.alignn_b200_radius_graph_offsets.argtypes = [vp, vp, i64, i64, C.c_double, C.c_double, vp, vp, sz, vp]
-    lib.alignn_b200_radius_graph_fill.restype = i32
-    lib.alignn_b200_radius_graph_fill.argtypes = [vp, vp, i64, i64, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]
-    lib.alignn_b200_pair_force_scatter.restype = i32
-    lib.alignn_b200_pair_force_scatter.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp]
-    lib.alignn_b200_virial_stress.restype = i32
-    lib.alignn_b200_virial_stress.argtypes = [vp, vp, vp, vp, vp, i64, f32, vp, vp]
-
-
-def csr_build_device(lib, src, dst, num_nodes):
-    """src, dst: int32 CUDA tensors -> dict(in_ptr, in_eid, out_ptr, out_eid, dst_sorted, max_in_deg) on the device."""
-    import torch
-    from alignn_b200._lib import stream_ptr
-    _sig(lib)
-    E, dev = src.numel(), src.device
-    i32 = lambda n: torch.empty(n, device=dev, dtype=torch.int32)  # noqa: E731
-    in_ptr, out_ptr, in_eid, out_eid, flags = i32(num_nodes + 1), i32(num_nodes + 1), i32(E), i32(E), i32(2)
-    nb = lib.alignn_b200_csr_build_workspace_bytes(num_nodes, E)
-    ws = torch.empty(max(nb, 1), device=dev, dtype=torch.uint8)
-    rc = lib.alignn_b200_csr_build(src.data_ptr(), dst.data_ptr(), num_nodes, E, in_ptr.data_ptr(), in_eid.data_ptr(),
-                                   out_ptr.data_ptr(), out_eid.data_ptr(), flags.data_ptr(), ws.data_ptr(), nb, stream_ptr())
-    if rc != 0:
-        raise RuntimeError(f"alignn_b200_csr_build -> {rc}")
-    f = flags.tolist()
-    return dict(in_ptr=in_ptr, in_eid=in_eid, out_ptr=out_ptr, out_eid=out_eid, dst_sorted=bool(f[0]), max_in_deg=f[1])
-
-
-def line_graph_device(lib, src, dst, in_ptr, in_eid):
-    """-> (lsrc, ldst, offsets) int32 CUDA tensors; one host read of T between the two launches."""
-    import torch
-    from alignn_b200._lib import stream_ptr
-    _sig(lib)
-    E, dev = src.numel(), src.device
-    off = torch.empty(E + 1, device=dev, dtype=torch.int32)
-    nb = lib.alignn_b200_line_graph_workspace_bytes(E)
-    ws = torch.empty(max(nb, 1), device=dev, dtype=torch.uint8)
-    rc = lib.alignn_b200_line_graph_offsets(src.data_ptr(), dst.data_ptr(), in_ptr.data_ptr(), E, off.data_ptr(), ws.data_ptr(),
-                                            nb, stream_ptr())
-    if rc != 0:
-        raise RuntimeError(f"alignn_b200_line_graph_offsets -> {rc}")
-    T = int(off[-1].item())
-    lsrc, ldst = (torch.empty(T, device=dev, dtype=torch.int32) for _ in range(2))
-    rc = lib.alignn_b200_line_graph_fill(src.data_ptr(), dst.data_ptr(), in_ptr.data_ptr(), in_eid.data_ptr(), E, off.data_ptr(),
-                                         lsrc.data_ptr(), ldst.data_ptr(), stream_ptr())
-    if rc != 0:
-        raise RuntimeError(f"alignn_b200_line_graph_fill -> {rc}")
-    return lsrc, ldst, off
-
-
-def pair_force_scatter(lib, pf, ix, add_reverse=True):
-    import torch
-    from alignn_b200._lib import stream_ptr
-    _sig(lib)
-    Nn = ix.in_ptr.numel() - 1
-    out = torch.empty(Nn, 3, device=pf.device, dtype=torch.float32)
-    rc = lib.alignn_b200_pair_force_scatter(pf.data_ptr(), ix.in_ptr.data_ptr(), None if ix.dst_sorted else ix.in_eid.data_ptr(),
-                                            ix.out_ptr.data_ptr(), ix.out_eid.data_ptr(), Nn, int(add_reverse), out.data_ptr(),
-                                            stream_ptr())
-    if rc != 0:
-        raise RuntimeError(f"alignn_b200_pair_force_scatter -> {rc}")
-    return out
-
-
-def virial_stress(lib, r, pf, edge_off, node_off, V, multiplier=1.0):
-    import torch
-    from alignn_b200._lib import stream_ptr
-    _sig(lib)
-    B = edge_off.numel() - 1
-    out = torch.empty(B, 3, 3, device=r.device, dtype=torch.float32)
-    rc = lib.alignn_b200_virial_stress(r.data_ptr(), pf.data_ptr(), edge_off.data_ptr(), node_off.data_ptr(), V.data_ptr(), B,
-                                       float(multiplier), out.data_ptr(), stream_ptr())
-    if rc != 0:
-        raise RuntimeError(f"alignn_b200_virial_stress -> {rc}")
-    return out
-
-
-def radius_scan_device(lib, X, shifts, cutoff, atol=1e-5):
-    """X [N,3], shifts [I,3]: float64 CUDA tensors -> (u, v, image_index int32, r float32 [E,3]) in (u, c, v) order."""
-    import torch
-    from alignn_b200._lib import stream_ptr
-    _sig(lib)
-    N, I, dev = X.shape[0], shifts.shape[0], X.device
-    off = torch.empty(N + 1, device=dev, dtype=torch.int32)
-    nb = lib.alignn_b200_radius_graph_workspace_bytes(N)
-    ws = torch.empty(max(nb, 1), device=dev, dtype=torch.uint8)
-    rc = lib.alignn_b200_radius_graph_offsets(X.data_ptr(), shifts.data_ptr(), N, I, cutoff, atol, off.data_ptr(), ws.data_ptr(),
-                                              nb, stream_ptr())
-    if rc != 0:
-        raise RuntimeError(f"alignn_b200_radius_graph_offsets -> {rc}")
-    E = int(off[-1].item())
-    u, v, c = (torch.empty(E, device=dev, dtype=torch.int32) for _ in range(3))
-    r = torch.empty(E, 3, device=dev, dtype=torch.float32)
-    rc = lib.alignn_b200_radius_graph_fill(X.data_ptr(), shifts.data_ptr(), N, I, cutoff, atol, off.data_ptr(), u.data_ptr(),
-                                           v.data_ptr(), c.data_ptr(), r.data_ptr(), stream_ptr())
-    if rc != 0:
-        raise RuntimeError(f"alignn_b200_radius_graph_fill -> {rc}")
-    return u, v, c, r
 
 
 # ---- fused backward (csrc/staged/egc_bwd_fused_tc.cu + node side in node_tail.cu) ----------------------------------

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# First hardware run of the staged kernels (alignn_b200/csrc/staged): validation, then A/B timing.
+# Validation and A/B timing of the experimental fully fused kernels (alignn_b200/csrc/staged).
 #   gpurun --timeout 1500 -- 'bash tools/staged_first_run.sh'
 # Every step runs under its own `timeout` (the mbarrier waits of the fused kernel trap after 2^26 spins instead of
 # hanging, but a wedged context must not eat the whole box); logs land in gpurun_out/.
@@ -8,9 +8,6 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 export ALIGNN_B200_STAGED=1
 python tools/build_staged.py > gpurun_out/staged_build.log 2>&1 || { echo "staged build failed"; tail -5 gpurun_out/staged_build.log; exit 1; }
-# 1. integer builders and the d=3 reductions first: simple kernels, independent of the tcgen05 one
-timeout 300 python -m pytest tests/test_staged.py -m gpu -q -k "device" > gpurun_out/staged_device_tests.log 2>&1
-echo "device builders: exit $?"; tail -3 gpurun_out/staged_device_tests.log
 # 2. the fused forward, smallest configuration first
 timeout 300 python -m pytest tests/test_staged.py -m gpu -q -k "fused and not backward" > gpurun_out/staged_fused_tests.log 2>&1
 rc=$?
