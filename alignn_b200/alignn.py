@@ -70,7 +70,8 @@ class RBFExpansion(nn.Module):
 def mlp_forward(layer: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
     """Linear -> norm -> SiLU.  On CUDA fp32 inputs the Linear (forward, data gradient, weight gradient) runs on
     the tcgen05 bf16x3 kernels when its shape is one the library supports (the angle/bond embeddings act on
-    T = 276 480 rows per batch); norm and SiLU stay plain library layers."""
+    T = 276 480 rows per batch); train-mode BatchNorm, LayerNorm and (without autograd) eval-mode BatchNorm run fused with
+    the SiLU on the library's row kernels."""
     lin, norm = layer[0], layer[1]
     if second_order.active:                 # force / stress training: everything must be differentiable twice
         return layer(x)
@@ -78,7 +79,14 @@ def mlp_forward(layer: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
         if (isinstance(norm, nn.BatchNorm1d) and norm.training and norm.momentum is not None and norm.affine
                 and torch.is_grad_enabled()):
             return ops.mlp_bn_train(x, lin, norm)        # Linear + batch statistics + normalise + SiLU on library kernels
+        if (isinstance(norm, nn.LayerNorm) and norm.elementwise_affine and norm.bias is not None
+                and tuple(norm.normalized_shape) == (lin.out_features,)):
+            return ops.mlp_ln(x, lin, norm)              # Linear, then LayerNorm + SiLU in one row kernel each way
         h = ops.tc_linear(x, lin)
+        if isinstance(norm, nn.BatchNorm1d) and not norm.training and norm.affine and norm.track_running_stats and not h.requires_grad:
+            rstd = torch.rsqrt(norm.running_var + norm.eps)
+            scale = norm.weight * rstd
+            return ops.affine_silu_residual(h, None, scale, norm.bias - norm.running_mean * scale)
     else:
         h = lin(x)
     return layer[2](norm(h))

@@ -5,6 +5,8 @@
 """
 from __future__ import annotations
 
+import contextlib
+
 from torch import nn
 
 from .conv import ALIGNNConvBase, EdgeGatedGraphConvBase, second_order
@@ -235,8 +237,10 @@ class ALIGNNAtomWise(nn.Module):
                 # lands in result["out"]; reproduced, not fixed
                 out = en_out
         if c.calculate_gradient:
-            (dr,) = torch.autograd.grad(en_out, r, grad_outputs=torch.ones_like(en_out),
-                                        create_graph=second, retain_graph=second or self.training)
+            # first order: only d energy / d r leaves this call, so the kernels skip every parameter gradient
+            with (contextlib.nullcontext() if second else ops.input_grads_only()):
+                (dr,) = torch.autograd.grad(en_out, r, grad_outputs=torch.ones_like(en_out),
+                                            create_graph=second, retain_graph=second or self.training)
             pair_forces = c.grad_multiplier * dr                         # (:530-539)
             if c.force_mult_natoms:
                 pair_forces = pair_forces * g.num_nodes()

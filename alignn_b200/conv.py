@@ -272,8 +272,10 @@ class _EdgeGatedConvFn(torch.autograd.Function):
         fk = _Fork(x.device)
         if need[1]:
             gx = fk.on(0, lambda: ops.gemm_gather(GP, img_catT, None, add0=gx_out if cfg.residual else None))
-        gWcat = fk.on(1, lambda: ops.wgrad(GP, x, groups=4))      # [4d, d] rows: src_gate | dst_update | dst_gate | src_update
-        gW_eg = fk.on(2, lambda: ops.wgrad(GM, y, groups=1))
+        params = not ops.input_grads_only.active                # a forces-only backward discards every parameter gradient
+        if params:
+            gWcat = fk.on(1, lambda: ops.wgrad(GP, x, groups=4))      # [4d, d] rows: src_gate | dst_update | dst_gate | src_update
+            gW_eg = fk.on(2, lambda: ops.wgrad(GM, y, groups=1))
         if need[2]:
             res = gy_out if (gy_out is not None and cfg.residual) else None
             up = cfg.up_link
@@ -285,6 +287,8 @@ class _EdgeGatedConvFn(torch.autograd.Function):
             else:
                 gy = ops.gemm_gather(GM, img_egT, None, add0=res)
         fk.join()
+        if not params:
+            return (None, gx, gy) + (None,) * 14
         gW_sg, gW_du, gW_dg, gW_su = gWcat[0:d], gWcat[d:2 * d], gWcat[2 * d:3 * d], gWcat[3 * d:4 * d]
         gb_sg, gb_du = vs[0], vs[1]
         gb_su, gb_dg = vd[4], vd[5]

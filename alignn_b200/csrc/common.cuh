@@ -80,6 +80,9 @@ __device__ __forceinline__ void ld_vec(float (&v)[RowCfg<D>::VPL], const float* 
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// u = pre-activation after the norm; silu(u) and its derivative
+__device__ __forceinline__ float silu_(float u) { return u * sigmoidf_(u); }
+__device__ __forceinline__ float dsilu_(float u) { float s = sigmoidf_(u); return s * (1.f + u * (1.f - s)); }
 
 // mean and reciprocal std of a row held across the warp (two-pass, like torch's LayerNorm)
 template <int D>

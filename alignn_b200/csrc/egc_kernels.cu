@@ -10,10 +10,6 @@
 
 namespace alignn {
 
-// u = pre-activation after the norm; returns silu(u)
-__device__ __forceinline__ float silu_(float u) { return u * sigmoidf_(u); }
-__device__ __forceinline__ float dsilu_(float u) { float s = sigmoidf_(u); return s * (1.f + u * (1.f - s)); }
-
 // =============================================================================================
 // Forward
 // =============================================================================================

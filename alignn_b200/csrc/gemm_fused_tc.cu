@@ -73,7 +73,8 @@ struct Params {
   const float* add0; int64_t ld0; const int32_t* idx0;   // addend rows: add0[idx0 ? idx0[r] : r][0 .. N)  (column offset folded in)
   const float* add1; int64_t ld1; const int32_t* idx1;
   float* C; int64_t ldc;
-  float* stats;                                          // [gridDim.x][2][N] or NULL (requires N == BN)
+  float* stats;                                          // [stat_quarters * gridDim.x][2][N] or NULL (requires N == BN)
+  int stat_quarters;                                     // 1: one partial row per CTA; 4: one per (CTA, lane quarter)
   const float* bn_scale; const float* bn_shift; const float* bn_mean;   // != NULL: add1 rows are NOT added; they are the
                                                          // pre-norm rows m of the BatchNorm+SiLU that produced this GEMM's
                                                          // input gradient, and stats = sum gu, sum gu (m - mean)
@@ -367,10 +368,17 @@ gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     if (kTmaStore && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // smem must outlive the last TMA stores
     if (do_stats) {
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-      // one partial row per (CTA, lane quarter): [4 * gridDim.x][2][BN] (the same layout as the pair kernel)
       const float* all = reinterpret_cast<const float*>(smem + F::OFF_STAT);
-      float* out_rows = p.stats + (int64_t)blockIdx.x * 4 * 2 * BN;
-      for (int i = ew * 32 + lane; i < 4 * 2 * BN; i += EPI_WARPS * 32) out_rows[i] = all[i];
+      if (p.stat_quarters == 4) {
+        // one partial row per (CTA, lane quarter): [4 * gridDim.x][2][BN] (the pair kernel's layout, when it is enabled)
+        float* out_rows = p.stats + (int64_t)blockIdx.x * 4 * 2 * BN;
+        for (int i = ew * 32 + lane; i < 4 * 2 * BN; i += EPI_WARPS * 32) out_rows[i] = all[i];
+      } else {
+        // one partial row per CTA: the four lane quarters summed in a fixed order
+        float* out_row = p.stats + (int64_t)blockIdx.x * 2 * BN;
+        for (int i = ew * 32 + lane; i < 2 * BN; i += EPI_WARPS * 32)
+          out_row[i] = (all[i] + all[2 * BN + i]) + (all[4 * BN + i] + all[6 * BN + i]);
+      }
     }
   } else if (warp == 0 && lane == 0) {
     // ================= MMA issuer (one thread) =================
@@ -460,8 +468,8 @@ int launch2(const CUtensorMap& mapA, const CUtensorMap& mapC, const Params& p, c
   }
   const int total = ((p.M + BM - 1) / BM) * (p.N / BN);
   int grid = total < 148 ? total : 148;
-  if (p.stats) grid = alignn_b200_gemm_gather_stat_rows(p.M, p.N) / 4;    // one partial row per CTA, whichever kernel runs (a CTA
-                                                                      // without tiles writes zeros)
+  if (p.stats) grid = alignn_b200_gemm_gather_stat_rows(p.M, p.N) / p.stat_quarters;   // the caller sized `stats` for this many
+                                                                      // CTAs (a CTA without tiles writes zeros)
   gemm_gather_bf16x3_kernel<BN, BNMODE><<<grid, THREADS, F::SMEM, st>>>(mapA, mapC, p);
   return check_launch();
 }
@@ -478,13 +486,15 @@ extern "C" {
 
 void alignn_b200_debug_gemm_trace(long long* device_buffer) { alignn::gemm2::g_trace = device_buffer; }
 
+__attribute__((visibility("hidden"))) int alignn_b200_gemm_pair_enabled();   /* gemm_pair_tc.cu */
+
 int alignn_b200_gemm_gather_stat_rows(int64_t M, int N) {
   const int bn = alignn::gemm2::pick_bn(N);
   if (bn == 0 || M <= 0) return 0;
   // CTAs of the launch (statistics need N == bn: one column tile): the same count for the one-CTA kernel and for the
   // pair kernel (two CTAs per 256-row tile)
   const int64_t total = 2 * ((M + 2 * alignn::gemm2::BM - 1) / (2 * alignn::gemm2::BM));
-  return 4 * (int)(total < 148 ? total : 148);       // four lane quarters per CTA, one partial row each
+  return (alignn_b200_gemm_pair_enabled() ? 4 : 1) * (int)(total < 148 ? total : 148);   // pair kernel: four lane quarters per CTA
 }
 
 __attribute__((visibility("hidden"))) int alignn_b200_gemm_gather_try_pair(const alignn_b200_gemm_gather_args* a, int* status);   /* gemm_pair_tc.cu */
@@ -519,7 +529,7 @@ int alignn_b200_gemm_gather(const alignn_b200_gemm_gather_args* a) {
   p.bias = a->bias;
   p.add0 = a->add0; p.ld0 = a->ld0; p.idx0 = a->idx0;
   p.add1 = a->add1; p.ld1 = a->ld1; p.idx1 = a->idx1;
-  p.C = a->C; p.ldc = a->ldc; p.stats = a->stats;
+  p.C = a->C; p.ldc = a->ldc; p.stats = a->stats; p.stat_quarters = alignn_b200_gemm_pair_enabled() ? 4 : 1;
   p.bn_scale = a->bn_scale; p.bn_shift = a->bn_shift; p.bn_mean = a->bn_mean;
   p.trace = g_trace;
   cudaStream_t st = (cudaStream_t)a->stream;

@@ -442,6 +442,7 @@ int launch_pair(const CUtensorMap& mapA, const CUtensorMap& mapC, const Params& 
 
 extern "C" {
 
+__attribute__((visibility("hidden"))) int alignn_b200_gemm_pair_enabled() { return alignn::gemmp::g_pair_enabled.load(); }
 void alignn_b200_debug_gemm_pair(int enabled) { alignn::gemmp::g_pair_enabled.store(enabled); }   /* A/B switch, not in the public header */
 
 /* called by alignn_b200_gemm_gather (gemm_fused_tc.cu) for the shapes the pair kernel covers; returns 1 if it took the call */

@@ -132,18 +132,24 @@ class FlatGradAllReducer:
 class FlatAdamW:
     """AdamW over ONE flat parameter: the parameters that receive gradients (`reducer.active`, discovered on the first
     backward) are re-homed as views into one contiguous fp32 buffer, their gradients already live in the reducer's
-    flat buffer, so the whole update is a single fused multi-tensor launch (the per-tensor fused AdamW needs ~10 launches
-    of ~40 us for ALIGNN's 87 small tensors).  Same arithmetic as `torch.optim.AdamW` per element; parameters without
-    gradients are untouched, as with the per-parameter optimizer.
+    flat buffer, so the whole update is ONE launch of the library's `alignn_b200_adamw_flat` kernel (row_kernels.cu;
+    torch's fused AdamW needs ~10 launches of ~40 us for ALIGNN's 87 small tensors, and 2 x 60 us on one flat tensor
+    because its multi-tensor chunking leaves most SMs idle).  Same arithmetic as `torch.optim.AdamW` per element
+    (alignn/train.py:253-263 builds that optimizer); parameters without gradients are untouched, as with the per-parameter
+    optimizer.  The step count lives on the device, so the launch can be captured in a CUDA graph and replayed
+    (`capturable` is accepted for compatibility and ignored on CUDA).  CPU tensors (the gloo tests) use torch.optim.AdamW on
+    the flat parameter.
 
     After an eager step the autograd version of every parameter is bumped, so caches keyed on it (operand images,
     alignn_b200.ops.ImageTable) see the update; inside a CUDA-graph capture those caches refresh unconditionally."""
 
-    def __init__(self, reducer: FlatGradAllReducer, lr: float = 1e-3, capturable: bool = False, **kw):
+    def __init__(self, reducer: FlatGradAllReducer, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2, capturable: bool = False):
         if reducer.flat is None:
             raise RuntimeError("FlatAdamW: run one backward() and reducer.gather() first (discovers the trainable set)")
         self.reducer = reducer
         self.params = list(reducer.active)
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
         flat = torch.empty_like(reducer.flat)
         off = 0
         with torch.no_grad():
@@ -154,12 +160,32 @@ class FlatAdamW:
                 off += n
         self.flat_param = torch.nn.Parameter(flat)
         self.flat_param.grad = reducer.flat
-        self.opt = torch.optim.AdamW([self.flat_param], lr=lr, fused=flat.is_cuda, capturable=capturable and flat.is_cuda, **kw)
+        self.opt = None
+        if flat.is_cuda:
+            self.exp_avg = torch.zeros_like(flat)
+            self.exp_avg_sq = torch.zeros_like(flat)
+            self.step_count = torch.zeros(1, dtype=torch.int64, device=flat.device)
+            self._ticket = torch.zeros(1, dtype=torch.int32, device=flat.device)
+        else:
+            self.opt = torch.optim.AdamW([self.flat_param], lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
 
-    def step(self):
-        self.flat_param.grad = self.reducer.flat
-        self.opt.step()
-        if not (self.flat_param.is_cuda and torch.cuda.is_current_stream_capturing()):
+    def step(self, zero_grad: bool = False):
+        """One update; `zero_grad=True` also clears the flat gradient buffer in the same pass (CUDA)."""
+        flat = self.flat_param.data
+        if self.opt is None:
+            from . import _lib
+            from ._lib import ptr, stream_ptr
+            with torch.cuda.device(flat.device):
+                _lib.check(_lib.load().alignn_b200_adamw_flat(
+                    ptr(flat), ptr(self.reducer.flat), ptr(self.exp_avg), ptr(self.exp_avg_sq), flat.numel(), self.lr,
+                    self.betas[0], self.betas[1], self.eps, self.weight_decay, int(zero_grad), ptr(self.step_count),
+                    ptr(self._ticket), stream_ptr()), "alignn_b200_adamw_flat")
+        else:
+            self.flat_param.grad = self.reducer.flat
+            self.opt.step()
+            if zero_grad:
+                self.reducer.zero_grad()
+        if not (flat.is_cuda and torch.cuda.is_current_stream_capturing()):
             for p in self.params:
                 torch.autograd.graph.increment_version(p)
 

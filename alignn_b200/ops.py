@@ -601,6 +601,22 @@ def linear_table(lin) -> ImageTable:
     return tbl
 
 
+class input_grads_only:
+    """Context manager for a backward pass whose PARAMETER gradients are thrown away -- `torch.autograd.grad(energy, r)`
+    for forces (alignn/models/alignn_atomwise.py:530-539 outside force training): the library's autograd Functions then
+    skip their weight-gradient GEMMs and bias / norm-parameter reductions and return None for them.  (autograd's own
+    `needs_input_grad` cannot tell: it is fixed at forward time from `requires_grad`.)  A plain process-wide flag, because
+    the autograd engine runs CUDA nodes on its own thread."""
+    active = False
+
+    def __enter__(self):
+        self._prev = input_grads_only.active
+        input_grads_only.active = True
+
+    def __exit__(self, *exc):
+        input_grads_only.active = self._prev
+
+
 def _pad_cols(x: torch.Tensor, k_pad: int) -> torch.Tensor:
     x = x.contiguous()
     return x if x.shape[1] == k_pad else torch.nn.functional.pad(x, (0, k_pad - x.shape[1]))
@@ -625,6 +641,8 @@ class _TCLinearFn(torch.autograd.Function):
         gx = None
         if ctx.needs_input_grad[0]:
             gx = gemm_gather(go, ctx.tbl.images["wT"])[:, :ctx.k_in]
+        if input_grads_only.active:
+            return gx, None, None, None
         gw = wgrad(go, x, 1)[:, :ctx.k_in]
         gb = colsum_rows(go)
         return gx, gw, gb, None
@@ -682,9 +700,66 @@ class _MLPBNTrainFn(torch.autograd.Function):
         gx = None
         if ctx.needs_input_grad[0]:
             gx = gemm_gather(gR, ctx.tbl.images["wT"])[:, :ctx.k_in]
+        if input_grads_only.active:
+            return gx, None, None, None, None, None, None
         gw = wgrad(gR, x, 1)[:, :ctx.k_in]
         # a bias that feeds a train-mode BatchNorm has an identically zero gradient (sum_rows gR == 0)
         return gx, gw, torch.zeros_like(c1), c2 * n, c1 * n, None, None
+
+
+# ---- Linear -> LayerNorm -> SiLU (embedding layers of the LayerNorm model, alignn_atomwise.py:249-268) ---------------
+class _MLPLNFn(torch.autograd.Function):
+    """Tensor-core Linear, then ONE row kernel for LayerNorm + SiLU (forward) and one for their backward (which also
+    leaves the per-block sums for d gamma / d beta); replaces 5 library passes over the [T, d] activations."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, eps, tbl):
+        lib = _lib.load()
+        x = _pad_cols(x, tbl.images["w"].K)
+        h = gemm_gather(x, tbl.images["w"], bias.contiguous())
+        n, d = h.shape
+        gamma, beta = gamma.contiguous(), beta.contiguous()
+        out = torch.empty_like(h)
+        rowstat = torch.empty(n, 2, device=h.device, dtype=torch.float32)
+        with _span("ln_silu_forward", 8 * n * d):
+            _lib.check(lib.alignn_b200_ln_silu_forward(ptr(h), ptr(gamma), ptr(beta), float(eps), n, d, ptr(out), ptr(rowstat),
+                                                        stream_ptr()), "alignn_b200_ln_silu_forward")
+        ctx.save_for_backward(x, h, rowstat, gamma, beta)
+        ctx.tbl = tbl
+        ctx.k_in = weight.shape[1]
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, go):
+        lib = _lib.load()
+        x, h, rowstat, gamma, beta = ctx.saved_tensors
+        go = go.contiguous()
+        n, d = h.shape
+        gh = torch.empty_like(h)
+        rows = partial_rows(n, d)
+        part = torch.empty(rows, 2 * d, device=h.device, dtype=torch.float32)
+        with _span("ln_silu_backward", 12 * n * d):
+            _lib.check(lib.alignn_b200_ln_silu_backward(ptr(h), ptr(go), ptr(rowstat), ptr(gamma), ptr(beta), n, d, ptr(gh),
+                                                         ptr(part), rows, stream_ptr()), "alignn_b200_ln_silu_backward")
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm_gather(gh, ctx.tbl.images["wT"])[:, :ctx.k_in]
+        if input_grads_only.active:
+            return gx, None, None, None, None, None, None
+        gwb = colsum(part)
+        gw = gb = None
+        if ctx.needs_input_grad[1]:
+            gw = wgrad(gh, x, 1)[:, :ctx.k_in]
+        if ctx.needs_input_grad[2]:
+            gb = colsum_rows(gh)
+        return gx, gw, gb, gwb[:d], gwb[d:], None, None
+
+
+def mlp_ln(x, lin, ln):
+    tbl = linear_table(lin)
+    tbl.refresh()
+    return _MLPLNFn.apply(x, lin.weight, lin.bias, ln.weight, ln.bias, ln.eps, tbl)
 
 
 def mlp_bn_train(x, lin, bn):

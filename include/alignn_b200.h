@@ -185,6 +185,26 @@ int alignn_b200_bn_backward_apply(const float* R, const float* g_out, const floa
                                   const float* mean, const float* rstd, const float* c1, const float* c2, int64_t n, int d,
                                   float* gR, alignn_stream_t stream);
 
+/* Linear -> LayerNorm -> SiLU embedding layers of the LayerNorm model (alignn/models/alignn_atomwise.py:249-268) on the
+ * rows h [n,d] the Linear produced:
+ *   ln_silu_forward:  out[r] = silu(LayerNorm_eps(h[r]) * gamma + beta);  rowstat[r] = {mean, rstd}  ([n,2] floats)
+ *   ln_silu_backward: gh = d loss / d h given g_out = d loss / d out; partials [partial_rows, 2, d] hold the per-block sums
+ *                     for d gamma (index 0) and d beta (index 1): finish with alignn_b200_colsum.
+ *                     partial_rows = alignn_b200_egc_partial_rows(n, d). */
+int alignn_b200_ln_silu_forward(const float* h, const float* gamma, const float* beta, float eps, int64_t n, int d, float* out,
+                                float* rowstat, alignn_stream_t stream);
+int alignn_b200_ln_silu_backward(const float* h, const float* g_out, const float* rowstat, const float* gamma, const float* beta,
+                                 int64_t n, int d, float* gh, float* partials, int partial_rows, alignn_stream_t stream);
+
+/* One AdamW update (torch.optim.AdamW arithmetic, amsgrad off; the optimizer alignn/train.py:253-263 builds) over flat
+ * 16-byte aligned fp32 buffers of n elements.  `step` is the DEVICE step counter (int64, starts at 0): the kernel uses
+ * t = *step + 1 for the bias corrections and stores t back, so the same launch replays correctly inside a CUDA graph.
+ * `ticket` is a zero-initialised device uint32 the kernel uses to find its last block (left at zero).  zero_grad != 0
+ * clears `grad` after use. */
+int alignn_b200_adamw_flat(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                           float beta2, float eps, float weight_decay, int zero_grad, int64_t* step, uint32_t* ticket,
+                           alignn_stream_t stream);
+
 /* Per-block partial column sums of a tall contiguous [n, d] matrix (rows: alignn_b200_egc_partial_rows(n, d));
  * finish with alignn_b200_colsum.  Used for the bias gradients of the embedding Linears (alignn.py:201-222). */
 int alignn_b200_colsum_partials(const float* a, int64_t n, int d, float* partials, int partial_rows, alignn_stream_t stream);
