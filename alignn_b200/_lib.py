@@ -130,6 +130,7 @@ _SIGNATURES = {
     "alignn_b200_virial_stress": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_float, _fp, _fp]),
     "alignn_b200_debug_gemm_flags": (None, [C.c_int]),
     "alignn_b200_debug_gemm_pair": (None, [C.c_int]),
+    "alignn_b200_debug_egc_flags": (None, [C.c_int]),
     "alignn_b200_debug_gemm_trace": (None, [_fp]),
     "alignn_b200_segment_mean": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, _fp, _fp]),
     "alignn_b200_segment_mean_backward": (C.c_int, [_fp, _fp, C.c_int64, C.c_int, _fp, _fp]),

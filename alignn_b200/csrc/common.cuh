@@ -79,7 +79,16 @@ __device__ __forceinline__ void ld_vec(float (&v)[RowCfg<D>::VPL], const float* 
   }
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// sigmoid in four instructions (FMUL, MUFU.EX2, FADD, MUFU.RCP; <= 2 ulp) instead of ~25 with an IEEE division and the
+// denormal paths of the non-ftz approximations: the edge kernels are bound by instruction issue at 4 warps per
+// scheduler, not by HBM (profiles/r02_ncu_full_summary.md).  exp(-x) underflowing to 0 and overflowing to +inf give
+// exactly 1 and 0.
+__device__ __forceinline__ float sigmoidf_(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
 // u = pre-activation after the norm; silu(u) and its derivative
 __device__ __forceinline__ float silu_(float u) { return u * sigmoidf_(u); }
 __device__ __forceinline__ float dsilu_(float u) { float s = sigmoidf_(u); return s * (1.f + u * (1.f - s)); }

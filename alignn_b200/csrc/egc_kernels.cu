@@ -180,6 +180,227 @@ egc_forward_kernel(alignn_b200_egc_fwd_args a) {
   }
 }
 
+// ---- forward, second pass, with the edge rows staged through shared memory -------------------------------------------
+// Same arithmetic, same per-row operation order and therefore the same bits as egc_forward_kernel<D, true>; what changes
+// is how the rows arrive.  Every warp owns a ring of kRing slots in shared memory; a slot holds the three rows of one
+// edge (gate m, gathered Bh[src], residual y) and is filled by cp.async (LDGSTS: global -> shared without passing through
+// registers), each lane copying exactly the 16-byte pieces it will read back, so completion needs no barrier -- only
+// cp.async.wait_group.  The warp issues the copies of edge i + kRing - 1 before it does the gate / norm / SiLU math of
+// edge i: kRing - 1 edges (9 KB at d = 256) stay in flight per warp WHILE it computes, where the register-staged kernel
+// has nothing in flight during the math of its two edges.  Slot headers (edge id, node, first / last flags) are
+// warp-uniform registers; the loop is unrolled over the ring so that they are indexed statically.
+constexpr int kRing = 4;
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async_piece(float* sdst, const float* gsrc) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sdst);
+  if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+  else if constexpr (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+template <int D>
+__device__ __forceinline__ void cp_async_row(float* srow, const float* __restrict__ grow, int lane) {
+  using C = RowCfg<D>;
+#pragma unroll
+  for (int c = 0; c < C::CH; ++c) cp_async_piece<C::W * 4>(srow + c * 32 * C::W + lane * C::W, grow + c * 32 * C::W + lane * C::W);
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 2)
+egc_forward_ring_kernel(alignn_b200_egc_fwd_args a) {
+  using C = RowCfg<D>;
+  constexpr int V = C::VPL;
+  constexpr int SLOT = 3 * D;
+  constexpr int F_FIRST = 1, F_LAST = 2, F_EMPTY = 4, F_DONE = 8;
+  extern __shared__ __align__(16) float dyn_smem[];
+  float* vec = dyn_smem;                                            // [4][D]: n_w, n_b, e_w, e_b
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* ring = dyn_smem + 4 * D + wib * kRing * SLOT;              // this warp's slots
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  const bool train = a.XP != nullptr;
+  const bool edge_out = a.y_out != nullptr;
+  const bool want_res = a.residual && edge_out;
+  const bool nstats = a.norm_nodes == ALIGNN_NORM_STATS;
+  {
+    const float* srcs[4] = {a.n_w, a.n_b, a.e_w, a.e_b};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      for (int i = threadIdx.x; i < D; i += blockDim.x) vec[q * D + i] = srcs[q] ? srcs[q][i] : 0.f;
+  }
+  __syncthreads();
+
+  // ---- producer cursor: (node, position in its in-edge list), indices of the current 32-edge chunk ----
+  // The index chain in_ptr[v] -> in_eid -> src is two or three dependent loads; it is requested one and two nodes ahead
+  // (n1*, n2*) so that moving to the next node never waits for it.
+  int64_t pv = warp0;
+  bool pdone = pv >= a.Nn;
+  int pfirst = 0, ppos = 0, pend = 0, cbase = 0, ccnt = 0, my_e = 0, my_s = 0;
+  int n1first = 0, n1end = 0, n1_e = 0, n1_s = 0, n2first = 0, n2end = 0;
+  auto load_ptr = [&](int64_t v, int& f, int& e) {
+    if (v < a.Nn) { f = a.in_ptr[v]; e = a.in_ptr[v + 1]; } else { f = 0; e = 0; }
+  };
+  auto load_idx = [&](int first, int end, int& e_out, int& s_out) {
+    if (lane < min(32, end - first)) {
+      e_out = a.in_eid ? a.in_eid[first + lane] : first + lane;
+      s_out = a.src[e_out];
+    }
+  };
+  load_ptr(pv, pfirst, pend);
+  ppos = cbase = pfirst;
+  ccnt = min(32, pend - pfirst);
+  load_idx(pfirst, pend, my_e, my_s);
+  load_ptr(pv + nwarps, n1first, n1end);
+  load_idx(n1first, n1end, n1_e, n1_s);
+  load_ptr(pv + 2 * nwarps, n2first, n2end);
+  int64_t hv[kRing];
+  int he[kRing], hf[kRing];
+
+  auto next_node = [&]() {
+    pv += nwarps;
+    pdone = pv >= a.Nn;
+    pfirst = ppos = cbase = n1first; pend = n1end;
+    ccnt = min(32, pend - pfirst);
+    my_e = n1_e; my_s = n1_s;
+    n1first = n2first; n1end = n2end;
+    load_idx(n1first, n1end, n1_e, n1_s);
+    load_ptr(pv + 2 * nwarps, n2first, n2end);
+  };
+  auto produce = [&](float* slot, int64_t& sv, int& se, int& sf) {
+    if (pdone) { sf = F_DONE; cp_async_commit(); return; }
+    sv = pv;
+    if (pend == pfirst) {                                           // a node without in-edges still gets its tail
+      se = -1; sf = F_FIRST | F_LAST | F_EMPTY;
+      cp_async_commit();
+      next_node();
+      return;
+    }
+    if (ppos >= cbase + ccnt) {
+      cbase = ppos;
+      ccnt = min(32, pend - ppos);
+      if (lane < ccnt) {
+        my_e = a.in_eid ? a.in_eid[cbase + lane] : cbase + lane;
+        my_s = a.src[my_e];
+      }
+    }
+    const int e = __shfl_sync(0xffffffffu, my_e, ppos - cbase), sidx = __shfl_sync(0xffffffffu, my_s, ppos - cbase);
+    cp_async_row<D>(slot, a.G + (int64_t)e * D, lane);
+    cp_async_row<D>(slot + D, a.P + (int64_t)sidx * 4 * D + D, lane);
+    if (want_res) cp_async_row<D>(slot + 2 * D, a.y + (int64_t)e * D, lane);
+    cp_async_commit();
+    se = e;
+    sf = (ppos == pfirst ? F_FIRST : 0) | (ppos + 1 == pend ? F_LAST : 0);
+    if (++ppos == pend) next_node();
+  };
+
+#pragma unroll
+  for (int s = 0; s < kRing - 1; ++s) produce(ring + s * SLOT, hv[s], he[s], hf[s]);
+  hf[kRing - 1] = F_DONE;
+
+  float accS[V], accSh[V], dv[V], xr[V], nst[2][V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { accS[k] = 0.f; accSh[k] = 0.f; dv[k] = 0.f; xr[k] = 0.f; nst[0][k] = 0.f; nst[1][k] = 0.f; }
+
+  bool running = true;
+  while (running) {
+#pragma unroll
+    for (int s = 0; s < kRing; ++s) {
+      // refill the slot consumed one step ago (slot s-1), then wait for slot s: kRing-1 groups may stay pending
+      {
+        const int t = (s + kRing - 1) % kRing;
+        produce(ring + t * SLOT, hv[t], he[t], hf[t]);
+      }
+      cp_async_wait<kRing - 1>();
+      const int f = hf[s];
+      if (f & F_DONE) { running = false; break; }
+      const int64_t v = hv[s];
+      float* slot = ring + s * SLOT;
+      if (f & F_FIRST) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) { accS[k] = 0.f; accSh[k] = 0.f; }
+        ld_row<D, false>(dv, a.P + v * 4 * D + 3 * D, lane);        // needed at the node's tail: requested a segment early
+        if (!nstats && a.residual) ld_row<D, false>(xr, a.x + v * D, lane);
+      }
+      if (!(f & F_EMPTY)) {
+        const int64_t e = he[s];
+        float m[V], cv[V];
+        ld_srow<D>(m, slot, lane);
+        ld_srow<D>(cv, slot + D, lane);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float sg = sigmoidf_(m[k]);
+          accS[k] += sg;
+          accSh[k] += cv[k] * sg;
+        }
+        if (edge_out) {
+          float o[V], ew[V], eb[V];
+          ld_srow<D>(ew, vec + 2 * D, lane);
+          ld_srow<D>(eb, vec + 3 * D, lane);
+          if (a.norm_edges == ALIGNN_NORM_LAYER) {
+            float mean, rstd;
+            row_mean_rstd<D>(m, a.ln_eps, mean, rstd);
+#pragma unroll
+            for (int k = 0; k < V; ++k) o[k] = silu_((m[k] - mean) * rstd * ew[k] + eb[k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < V; ++k) o[k] = silu_(m[k] * ew[k] + eb[k]);
+          }
+          if (a.residual) {
+            float yr[V];
+            ld_srow<D>(yr, slot + 2 * D, lane);
+#pragma unroll
+            for (int k = 0; k < V; ++k) o[k] += yr[k];
+          }
+          st_row<D, true>(a.y_out + e * D, o, lane);
+        }
+      }
+      if (f & F_LAST) {
+        // ---- node tail: h = Sh/(S+eps); x' = src_update(x) + h; norm; silu; residual ----
+        float xp[V], h[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) { h[k] = accSh[k] / (accS[k] + a.gate_eps); xp[k] = dv[k] + h[k]; }
+        if (train) {
+          st_row<D, false>(a.XP + v * D, xp, lane);
+          st_row<D, false>(a.S + v * D, accS, lane);
+          st_row<D, false>(a.H + v * D, h, lane);
+        }
+        if (nstats) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) { nst[0][k] += xp[k]; nst[1][k] += xp[k] * xp[k]; }
+        } else {
+          float o[V], nw[V], nb[V];
+          ld_srow<D>(nw, vec, lane);
+          ld_srow<D>(nb, vec + D, lane);
+          if (a.norm_nodes == ALIGNN_NORM_LAYER) {
+            float mean, rstd;
+            row_mean_rstd<D>(xp, a.ln_eps, mean, rstd);
+#pragma unroll
+            for (int k = 0; k < V; ++k) o[k] = silu_((xp[k] - mean) * rstd * nw[k] + nb[k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < V; ++k) o[k] = silu_(xp[k] * nw[k] + nb[k]);
+          }
+          if (a.residual) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) o[k] += xr[k];
+          }
+          st_row<D, false>(a.x_out + v * D, o, lane);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  if (a.partials) {   // {0, 0, sum x', sum x'^2}: the edge statistics came from the gather GEMM
+    __syncthreads();
+    float* out_row = a.partials + (int64_t)blockIdx.x * 4 * D;
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) out_row[i] = 0.f;
+    block_reduce_to_partials<D, 2>(nst, out_row + 2 * D, dyn_smem + 4 * D);
+  }
+}
+
 // =============================================================================================
 // Backward, destination-keyed pass: node-norm backward, per-edge gate backward, edge-norm
 // backward, GM = dL/dm, GP[:, 2d:3d] = sum over in-edges (dL/d e_dst), GP[:, 3d:4d] = dL/dx'.
@@ -739,6 +960,8 @@ int record_cuda_error(int e) { g_last_cuda_error.store(e); return ALIGNN_ERR_CUD
 namespace {
 using alignn::check_launch;
 using alignn::g_launches;
+std::atomic<int> g_forward_ring{1};      // A/B switches (alignn_b200_debug_egc_flags: bit 0 / bit 1 select the register-staged kernels)
+std::atomic<int> g_backward_ring{1};
 using alignn::g_last_cuda_error;
 inline bool supported_d(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
 inline int grid_for_rows(int64_t n) {
@@ -776,6 +999,7 @@ const char* alignn_b200_strerror(int s) {
 }
 
 int alignn_b200_last_cuda_error(void) { return g_last_cuda_error.load(); }
+void alignn_b200_debug_egc_flags(int flags) { g_forward_ring.store((flags & 1) ? 0 : 1); g_backward_ring.store((flags & 2) ? 0 : 1); }
 uint64_t alignn_b200_launch_count(void) { return g_launches.load(); }
 
 int alignn_b200_egc_partial_rows(int64_t Nn, int d) { (void)d; return grid_for_rows(Nn); }
@@ -799,7 +1023,18 @@ int alignn_b200_egc_forward(const alignn_b200_egc_fwd_args* a) {
   const int grid = grid_for_rows(a->Nn);
   DISPATCH_D(a->d, {
     const size_t smem_bytes = (size_t)(4 + (a->partials ? alignn::kWarpsPerBlock * 4 : 0)) * D * sizeof(float);
-    if (a->gate_is_m) alignn::egc_forward_kernel<D, true><<<grid, alignn::kThreads, smem_bytes, st>>>(*a);
+    if (a->gate_is_m && g_forward_ring.load()) {
+      // rows staged through a shared-memory ring (cp.async); same results as egc_forward_kernel<D, true>
+      const size_t ring_bytes = (size_t)(4 + alignn::kWarpsPerBlock * alignn::kRing * 3) * D * sizeof(float);
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(alignn::egc_forward_ring_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)ring_bytes);
+        if (e != cudaSuccess) return alignn::record_cuda_error((int)e);
+        configured = true;
+      }
+      alignn::egc_forward_ring_kernel<D><<<grid, alignn::kThreads, ring_bytes, st>>>(*a);
+    } else if (a->gate_is_m) alignn::egc_forward_kernel<D, true><<<grid, alignn::kThreads, smem_bytes, st>>>(*a);
     else alignn::egc_forward_kernel<D, false><<<grid, alignn::kThreads, smem_bytes, st>>>(*a);   // <= 36 KB: no opt-in needed
   });
   return check_launch();

@@ -87,7 +87,9 @@ struct Params {
 __host__ __device__ constexpr int plane_off(int r, int k) { return (r >> 3) * (int)SBO + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2; }
 
 __device__ __forceinline__ float dsilu_(float u) {          // d/du [u * sigmoid(u)], same formula as egc_kernels.cu
-  const float sg = 1.f / (1.f + __expf(-u));
+  float e, sg;                                             // 4-instruction sigmoid, as common.cuh's sigmoidf_
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.f + e));
   return sg * (1.f + u * (1.f - sg));
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {

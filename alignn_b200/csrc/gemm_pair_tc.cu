@@ -81,7 +81,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ float dsilu_(float u) { const float sg = 1.f / (1.f + __expf(-u)); return sg * (1.f + u * (1.f - sg)); }
+__device__ __forceinline__ float dsilu_(float u) { float e, sg;                                             // 4-instruction sigmoid, as common.cuh's sigmoidf_
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.f + e)); return sg * (1.f + u * (1.f - sg)); }
 
 // ---- cluster plumbing -------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }

@@ -6,6 +6,7 @@ tensors or if the library reports an error -- there is no fallback path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from typing import Optional, Tuple
 
@@ -178,7 +179,7 @@ class BNLink:
 # Measured on B200 (batch 64, d = 256): the data-gradient GEMM with the two extra reductions in its epilogue takes 535 us
 # instead of 225 us -- the epilogue of the tensor-core kernels is already the saturated agent (shared-memory / L1 pipe,
 # DESIGN.md section 4) -- while the reduction pass it replaces costs 121 us.  Off by default; kept for A/B runs.
-USE_BN_LINKS = False
+USE_BN_LINKS = os.environ.get("ALIGNN_B200_BN_LINKS", "0") == "1"
 
 
 def bn_backward_finish(partials: torch.Tensor, n: int, rstd: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

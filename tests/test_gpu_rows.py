@@ -154,3 +154,48 @@ def test_flat_adamw_replays_inside_a_cuda_graph():
     assert opt.step_count.item() == 3
     for pa, pb in zip(a.parameters(), b.parameters()):
         assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-6)
+
+
+# ---- ring-staged edge kernels (cp.async into shared memory) are the register-staged kernels, bit for bit -------------
+@pytest.mark.parametrize("d", [32, 64, 128, 256])
+@pytest.mark.parametrize("mode", ["bn_train", "layernorm", "affine_inference"])
+def test_forward_ring_kernel_is_bit_identical_to_register_kernel(d, mode):
+    from alignn_b200._lib import NORM_AFFINE, NORM_LAYER, NORM_STATS
+    from alignn_b200.graph import Graph
+    lib = _lib.load()
+    gen = torch.Generator(device="cpu").manual_seed(d)
+    Nn = 301
+    # ragged in-degrees: empty nodes, one node with 70 in-edges (> one 32-edge chunk), edges in random order (in_eid used)
+    deg = torch.randint(0, 9, (Nn,), generator=gen)
+    deg[5] = 70
+    deg[0] = 0
+    deg[Nn - 1] = 0
+    dst = torch.repeat_interleave(torch.arange(Nn), deg)
+    perm = torch.randperm(dst.numel(), generator=gen)
+    dst = dst[perm]
+    src = torch.randint(0, Nn, (dst.numel(),), generator=gen)
+    for sort in (False, True):
+        if sort:
+            order = torch.argsort(dst, stable=True)
+            src, dst = src[order], dst[order]
+        gr = Graph(src.numpy(), dst.numpy(), Nn).to(DEV)
+        ix = gr.index
+        Ne = dst.numel()
+        rnd = lambda *s: torch.randn(*s, generator=gen).to(DEV)  # noqa: E731
+        x, y, G, P = rnd(Nn, d), rnd(Ne, d), rnd(Ne, d), rnd(Nn, 4 * d)
+        vec = [torch.rand(d, generator=gen).to(DEV) + 0.5 for _ in range(4)]
+        nn_, ne_, save = {"bn_train": (NORM_STATS, NORM_AFFINE, True), "layernorm": (NORM_LAYER, NORM_LAYER, True),
+                          "affine_inference": (NORM_AFFINE, NORM_AFFINE, False)}[mode]
+        res = {}
+        try:
+            for flag in (1, 0):
+                lib.alignn_b200_debug_egc_flags(flag)
+                res[flag] = ops.egc_forward(ix, x, y, G, P, *vec, norm_nodes=nn_, norm_edges=ne_, residual=True, save=save,
+                                            need_edge_out=True, gate_is_m=True)
+        finally:
+            lib.alignn_b200_debug_egc_flags(0)
+        for k in ("x_out", "y_out", "XP", "S", "H", "partials"):
+            a, b = res[0][k], res[1][k]
+            assert (a is None) == (b is None), k
+            if a is not None:
+                assert torch.equal(a, b), (k, sort)
