@@ -71,6 +71,10 @@ class GemmGatherArgs(C.Structure):
     ]
 
 
+class WgradProblem(C.Structure):
+    _fields_ = [("A", _fp), ("lda", C.c_int64), ("B", _fp), ("ldb", C.c_int64), ("K", C.c_int64), ("out", _fp), ("ld_out", C.c_int64)]
+
+
 class ImageEntry(C.Structure):
     _fields_ = [("W", _fp), ("ldw", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32), ("transpose", C.c_int32),
                 ("n_off", C.c_int32), ("k_off", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("image", _fp)]
@@ -110,6 +114,8 @@ _SIGNATURES = {
     "alignn_b200_gemm_gather": (C.c_int, [C.POINTER(GemmGatherArgs)]),
     "alignn_b200_gemm_gather_stat_rows": (C.c_int, [C.c_int64, C.c_int]),
     "alignn_b200_wgrad_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int, C.c_int]),
+    "alignn_b200_wgrad_batch_workspace_bytes": (C.c_size_t, [C.POINTER(WgradProblem), C.c_int, C.c_int]),
+    "alignn_b200_wgrad_batch": (C.c_int, [C.POINTER(WgradProblem), C.c_int, C.c_int, _fp, C.c_size_t, _fp]),
     "alignn_b200_wgrad": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _fp, C.c_int64,
                                     _fp, C.c_size_t, _fp]),
     "alignn_b200_csr_build_host": (C.c_int, [_fp, _fp, C.c_int64, C.c_int64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),

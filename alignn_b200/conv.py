@@ -223,6 +223,7 @@ class _EdgeGatedConvFn(torch.autograd.Function):
                 cfg.images = None
                 cfg.legacy_w = (Wcat, W_eg)
             ctx.save_for_backward(x, y, P, out["M"], out["XP"], out["S"], out["H"], nw, nb, ew, eb)
+            ctx.weights = (W_sg, W_dg, W_eg, W_su, W_du)          # identities only: ops.WgradQueue maps them to destinations
         ctx.y_dead = y_out is None
         if y_out is None:       # dead edge output (or an edgeless graph): hand autograd an empty placeholder
             y_out = x.new_empty((0, d))
@@ -273,7 +274,15 @@ class _EdgeGatedConvFn(torch.autograd.Function):
         if need[1]:
             gx = fk.on(0, lambda: ops.gemm_gather(GP, img_catT, None, add0=gx_out if cfg.residual else None))
         params = not ops.input_grads_only.active                # a forces-only backward discards every parameter gradient
-        if params:
+        queue = ops.WgradQueue.current
+        W_sg, W_dg, W_eg, W_su, W_du = ctx.weights
+        deferred = params and queue is not None and ops.wgrad_supported(d, d) and queue.wants(W_sg, W_du, W_dg, W_su, W_eg)
+        if deferred:
+            # weight gradients are off the critical path: queued, computed by ONE batched launch at the end of backward
+            for j, W in enumerate((W_sg, W_du, W_dg, W_su)):           # column blocks of GP: e_src | Bh | e_dst | src_update
+                queue.add(GP[:, j * d:(j + 1) * d], x, W)
+            queue.add(GM, y, W_eg)
+        elif params:
             gWcat = fk.on(1, lambda: ops.wgrad(GP, x, groups=4))      # [4d, d] rows: src_gate | dst_update | dst_gate | src_update
             gW_eg = fk.on(2, lambda: ops.wgrad(GM, y, groups=1))
         if need[2]:
@@ -289,7 +298,10 @@ class _EdgeGatedConvFn(torch.autograd.Function):
         fk.join()
         if not params:
             return (None, gx, gy) + (None,) * 14
-        gW_sg, gW_du, gW_dg, gW_su = gWcat[0:d], gWcat[d:2 * d], gWcat[2 * d:3 * d], gWcat[3 * d:4 * d]
+        if deferred:
+            gW_sg = gW_du = gW_dg = gW_su = gW_eg = None
+        else:
+            gW_sg, gW_du, gW_dg, gW_su = gWcat[0:d], gWcat[d:2 * d], gWcat[2 * d:3 * d], gWcat[3 * d:4 * d]
         gb_sg, gb_du = vs[0], vs[1]
         gb_su, gb_dg = vd[4], vd[5]
         gb_eg = gb_dg                           # sum_e gm_e == sum_v sum_{e->v} gm_e

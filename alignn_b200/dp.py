@@ -64,6 +64,7 @@ class FlatGradAllReducer:
         self.views: List[torch.Tensor] = []
         self.active: List[torch.nn.Parameter] = []
         self._work = None
+        self.queue = None            # ops.WgradQueue once `deferring()` has been used
 
     @property
     def world_size(self) -> int:
@@ -83,6 +84,35 @@ class FlatGradAllReducer:
         for p in self.active:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+        self._refresh_queue()
+
+    def _refresh_queue(self) -> None:
+        """(Re)build the destination map of the deferred weight gradients: parameter storage -> its slice of the flat
+        gradient buffer.  Called again by FlatAdamW after it re-homed the parameters (their data_ptr changed)."""
+        if self.queue is None or self.flat is None or not self.flat.is_cuda:
+            return
+        self.queue.dest = {p.data_ptr(): v for p, v in zip(self.active, self.views)
+                           if p.dim() == 2 and p.shape[0] == p.shape[1] and v.data_ptr() % 16 == 0}
+
+    def deferring(self):
+        """Context manager for `loss.backward()`: the conv layers queue their weight-gradient GEMMs instead of launching
+        them one by one, and `gather()` runs the whole queue as ONE batched launch that writes straight into the flat
+        buffer (alignn_b200.ops.WgradQueue / alignn_b200_wgrad_batch).  No effect before the flat buffer exists (first
+        backward) or on CPU tensors."""
+        from . import ops
+        red = self
+
+        class _Ctx:
+            def __enter__(self):
+                if red.queue is None:
+                    red.queue = ops.WgradQueue()
+                    red._refresh_queue()
+                self.prev = ops.WgradQueue.current
+                ops.WgradQueue.current = red.queue
+
+            def __exit__(self, *exc):
+                ops.WgradQueue.current = self.prev
+        return _Ctx()
 
     def zero_grad(self) -> None:
         """Drop the gradients: autograd then WRITES fresh gradient tensors during backward instead of launching one
@@ -95,10 +125,21 @@ class FlatGradAllReducer:
         alias its slice, so the collective and the optimizer both work on the flat buffer."""
         if self.flat is None:
             self._build()
-        grads = [p.grad for p in self.active]
-        if any(g is None for g in grads):
-            raise RuntimeError("a parameter that used to receive a gradient did not get one this step")
-        torch._foreach_copy_(self.views, grads)
+        deferred = set()
+        if self.queue is not None:
+            deferred = set(self.queue.deferred_ptrs())
+            self.queue.flush()                      # one batched launch; results land in their slices of `flat`
+        views, grads = [], []
+        for p, v in zip(self.active, self.views):
+            if p.data_ptr() in deferred:
+                if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                    v.add_(p.grad)                  # the weight was also used outside the queue in this backward
+                continue
+            if p.grad is None:
+                raise RuntimeError("a parameter that used to receive a gradient did not get one this step")
+            views.append(v)
+            grads.append(p.grad)
+        torch._foreach_copy_(views, grads)
         for p, v in zip(self.active, self.views):
             p.grad = v
 
@@ -168,6 +209,7 @@ class FlatAdamW:
             self._ticket = torch.zeros(1, dtype=torch.int32, device=flat.device)
         else:
             self.opt = torch.optim.AdamW([self.flat_param], lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        reducer._refresh_queue()                    # parameters moved: deferred weight gradients are keyed by storage
 
     def step(self, zero_grad: bool = False):
         """One update; `zero_grad=True` also clears the flat gradient buffer in the same pass (CUDA)."""

@@ -576,6 +576,71 @@ def wgrad(A: torch.Tensor, B: torch.Tensor, groups: int = 1) -> torch.Tensor:
     return out
 
 
+WGRAD_BATCH_MAX = 64      # problems per launch (kMaxProblems in csrc/wgrad_tc.cu)
+
+
+def wgrad_batch(problems) -> None:
+    """ONE launch for many square weight gradients: `problems` is a list of (A [K, >= d] view, B [K, >= d] view, out [d, d]
+    view); out[o, i] = sum_r A[r, o] * B[r, i].  Views may be column slices of wider matrices (row stride = stride(0))."""
+    lib = _lib.load()
+    if not problems:
+        return
+    d = problems[0][2].shape[0]
+    for i0 in range(0, len(problems), WGRAD_BATCH_MAX):
+        chunk = problems[i0:i0 + WGRAD_BATCH_MAX]
+        arr = (_lib.WgradProblem * len(chunk))()
+        nbytes_in = 0
+        for q, (A, B, out) in zip(arr, chunk):
+            if not (A.is_cuda and B.is_cuda and out.is_cuda and A.dtype == B.dtype == out.dtype == torch.float32):
+                raise RuntimeError("alignn_b200 kernels need fp32 CUDA tensors")
+            if out.shape != (d, d) or A.shape[1] != d or B.shape[1] != d or A.shape[0] != B.shape[0] or A.stride(1) != 1 \
+                    or B.stride(1) != 1 or out.stride(1) != 1:
+                raise RuntimeError("wgrad_batch: every problem is A [K, d], B [K, d] -> out [d, d] with unit column stride")
+            q.A, q.lda, q.B, q.ldb, q.K = ptr(A), A.stride(0), ptr(B), B.stride(0), A.shape[0]
+            q.out, q.ld_out = ptr(out), out.stride(0)
+            nbytes_in += 8 * A.shape[0] * d
+        nbytes = int(lib.alignn_b200_wgrad_batch_workspace_bytes(arr, len(chunk), d))
+        if nbytes == 0:
+            raise RuntimeError(f"alignn_b200 wgrad_batch: unsupported batch (d={d}, n={len(chunk)})")
+        # the non-cooperative fallback runs problem by problem and needs the single-problem workspace
+        nbytes = max(nbytes, max(int(lib.alignn_b200_wgrad_workspace_bytes(A.shape[0], d, d, 1)) for A, _, _ in chunk))
+        ws = torch.empty(nbytes, device=chunk[0][0].device, dtype=torch.uint8)
+        with _span(f"wgrad_batch<{d}>", nbytes_in):
+            _lib.check(lib.alignn_b200_wgrad_batch(arr, len(chunk), d, ptr_any(ws), nbytes, stream_ptr()), "alignn_b200_wgrad_batch")
+
+
+class WgradQueue:
+    """Deferred weight gradients.  While a queue is installed (`WgradQueue.current`), the conv Functions do not launch their
+    weight-gradient GEMMs during backward; they register (A, B, destination) here and return None for those weights, and
+    `flush()` computes all of them with one `wgrad_batch` launch, writing straight into the destinations -- slices of
+    the flat gradient buffer of `alignn_b200.dp.FlatGradAllReducer`, which installs the queue.  A weight is only deferred
+    if the queue knows a destination for it (`dest`: parameter data_ptr -> [d, d] view) and it has not been queued already
+    in this backward (a layer applied twice falls back to the immediate path and autograd's accumulation)."""
+    current: Optional["WgradQueue"] = None
+
+    def __init__(self):
+        self.dest = {}            # weight.data_ptr() -> destination view
+        self.items = []           # (A, B, out)
+        self._seen = set()
+
+    def wants(self, *weights) -> bool:
+        keys = [w.data_ptr() for w in weights]
+        return all(k in self.dest and k not in self._seen for k in keys) and len(set(keys)) == len(keys)
+
+    def add(self, A: torch.Tensor, B: torch.Tensor, weight: torch.Tensor) -> None:
+        k = weight.data_ptr()
+        self._seen.add(k)
+        self.items.append((A, B, self.dest[k]))
+
+    def deferred_ptrs(self):
+        return self._seen
+
+    def flush(self) -> None:
+        items, self.items = self.items, []
+        self._seen = set()
+        wgrad_batch(items)
+
+
 def colsum_rows(a: torch.Tensor) -> torch.Tensor:
     """Column sums of a tall contiguous [n, d] matrix, deterministic two-stage reduction."""
     lib = _lib.load()

@@ -257,7 +257,8 @@ def run_ours(args):
         reducer.zero_grad()
         out = model((g, lg, lat))
         loss = (out - tgt).abs().mean()                      # nn.L1Loss, train.py:240
-        loss.backward()
+        with reducer.deferring():                            # weight-gradient GEMMs queued: one batched launch in gather()
+            loss.backward()
         reducer.all_reduce()
         opt.step()
         return loss
@@ -347,8 +348,9 @@ def run_ours(args):
         reducer.zero_grad()
         out = model((g, lg, lat))
         loss = (out - tgt).abs().mean()
-        loss.backward()
-        reducer.gather()                                      # gradients -> flat buffer (one multi-tensor copy)
+        with reducer.deferring():
+            loss.backward()
+        reducer.gather()                                      # batched weight gradients + the other gradients -> flat buffer
         if nccl_in_graph:
             reducer.reduce_flat()
             opt.step()

@@ -300,6 +300,23 @@ size_t alignn_b200_wgrad_workspace_bytes(int64_t K, int DA, int DB, int groups);
 int alignn_b200_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int DA, int DB, int groups,
                       float* out, int64_t ld_out, void* workspace, size_t workspace_bytes, alignn_stream_t stream);
 
+/* Many square weight gradients in ONE launch: out_p[o, i] = sum_{r < K_p} A_p[r, o] * B_p[r, i], o, i < D, for every
+ * problem p < n (n <= 64).  The 4+4 stack's backward pass produces 24 such products per step (GP^T x
+ * per projection, GM^T y), none on its critical path; queued and launched together the small ones (K = atoms or bonds)
+ * ride along at the memory rate instead of paying a launch prologue and a grid barrier each.  `problems` is a HOST array
+ * (copied into the kernel parameters: capturable in a CUDA graph); A, B, out are device pointers, 16-byte aligned,
+ * leading dimensions multiples of 4.  Deterministic (fixed-order split-K).  The fallback on a device that cannot
+ * co-schedule 148 CTAs runs the problems one by one through alignn_b200_wgrad and needs that function's workspace. */
+typedef struct {
+  const float* A; int64_t lda;     /* [K, >= D] output-gradient rows                                   */
+  const float* B; int64_t ldb;     /* [K, >= D] input rows                                             */
+  int64_t K;
+  float* out; int64_t ld_out;      /* [D, D] weight gradient, row o = output channel                   */
+} alignn_b200_wgrad_problem;
+size_t alignn_b200_wgrad_batch_workspace_bytes(const alignn_b200_wgrad_problem* problems, int n, int D);
+int alignn_b200_wgrad_batch(const alignn_b200_wgrad_problem* problems, int n, int D, void* workspace, size_t workspace_bytes,
+                            alignn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Host-side structure builders (plain CPU code, host pointers, no stream; usable without a GPU).
  * Replace the structure step DGL does on the CPU for the reference: `dgl.graph((u, v))` + CSR/CSC views

@@ -145,3 +145,77 @@ def test_gemm_gather_residual_and_strided_views():
     out = ops.gemm_gather(A, img_t, None, add0=R)
     ref = A.double() @ W.double() + R.double()
     assert (out.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+
+
+# ---- wgrad_batch: many square weight gradients in one launch (csrc/wgrad_tc.cu, alignn_b200_wgrad_batch) ------------
+@pytest.mark.parametrize("d", [256, 64, 32])
+def test_wgrad_batch_matches_fp64_and_is_deterministic(d):
+    g = torch.Generator(device="cpu").manual_seed(d)
+    Ks = [0, 1, 31, 33, 1920, 1920, 23040, 5000, 70001, 128, 276480 if d == 256 else 40000]
+    problems, refs = [], []
+    for i, K in enumerate(Ks):
+        wide = torch.randn(K, 4 * d, generator=g).to(DEV)                 # A is a column block of a wider matrix (GP)
+        A = wide[:, (i % 4) * d:(i % 4 + 1) * d]
+        B = torch.randn(K, d, generator=g).to(DEV)
+        out = torch.full((d, d), float("nan"), device=DEV)
+        problems.append((A, B, out))
+        refs.append(A.double().t() @ B.double())
+    ops.wgrad_batch(problems)
+    first = [p[2].clone() for p in problems]
+    for (A, B, out), ref, K in zip(problems, refs, Ks):
+        assert torch.isfinite(out).all()
+        err = (out.double() - ref).abs().max().item()
+        assert err <= 2e-5 * max(ref.abs().max().item(), 1e-30) + (0 if K else 0), (K, err)
+        if K:
+            # same products as the single-problem kernel up to the order of the split-K partial sums
+            single = ops.wgrad(A.contiguous(), B, 1)
+            assert (out - single).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    ops.wgrad_batch(problems)
+    for a, (_, _, out) in zip(first, problems):
+        assert torch.equal(a, out)
+
+
+def test_wgrad_batch_more_problems_than_one_launch_holds():
+    g = torch.Generator(device="cpu").manual_seed(1)
+    d = 64
+    problems, refs = [], []
+    for i in range(ops.WGRAD_BATCH_MAX + 7):
+        K = 50 + 13 * i
+        A, B = torch.randn(K, d, generator=g).to(DEV), torch.randn(K, d, generator=g).to(DEV)
+        problems.append((A, B, torch.empty(d, d, device=DEV)))
+        refs.append(A.double().t() @ B.double())
+    ops.wgrad_batch(problems)
+    for (_, _, out), ref in zip(problems, refs):
+        assert (out.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+
+
+def test_deferred_weight_gradients_equal_immediate_ones():
+    """FlatGradAllReducer.deferring(): the conv layers queue their weight gradients, gather() computes them with one
+    batched launch into the flat buffer.  Same gradients as the launch-by-launch path (split-K order differs)."""
+    from alignn_b200 import dp, synthetic
+    from alignn_b200.alignn import ALIGNN, ALIGNNConfig
+    g, lg, lat, tgt = (t.to(DEV) for t in synthetic.make_batch(6, 9, 12, seed=5, vary_atoms=True))
+    flats = []
+    launches = []
+    for deferred in (False, True):
+        torch.manual_seed(0)
+        model = ALIGNN(ALIGNNConfig(name="alignn", alignn_layers=2, gcn_layers=2, hidden_features=64, embedding_features=32)).to(DEV).train()
+        red = dp.FlatGradAllReducer(model.parameters())
+        for it in range(2):                                            # the first backward discovers the trainable set
+            red.zero_grad()
+            loss = (model((g, lg, lat)) - tgt).abs().mean()
+            from alignn_b200 import _lib
+            l0 = _lib.launch_count()
+            if deferred:
+                with red.deferring():
+                    loss.backward()
+            else:
+                loss.backward()
+            red.gather()
+            l1 = _lib.launch_count()
+        flats.append(red.flat.clone())
+        launches.append(l1 - l0)
+        assert all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(red.active, red.views))
+    a, b = flats
+    assert (a - b).abs().max().item() <= 2e-5 * a.abs().max().item()
+    assert launches[1] < launches[0] - 10                               # 4 convs x (2 launches -> 0) + ... -> 1 batched launch
