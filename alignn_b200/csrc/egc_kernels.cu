@@ -595,7 +595,7 @@ egc_backward_dst_kernel(alignn_b200_egc_bwd_args a) {
 // =============================================================================================
 template <int D>
 __global__ void __launch_bounds__(kThreads)
-egc_backward_src_kernel(alignn_b200_egc_bwd_args a, float* __restrict__ partials_src) {
+egc_backward_src_kernel(alignn_b200_egc_bwd_args a, float* __restrict__ partials_src, int partial_rows_total) {
   using C = RowCfg<D>;
   constexpr int V = C::VPL;
   __shared__ float red[kWarpsPerBlock * D];
@@ -655,7 +655,12 @@ egc_backward_src_kernel(alignn_b200_egc_bwd_args a, float* __restrict__ partials
 #pragma unroll
     for (int k = 0; k < V; ++k) { acc[0][k] += accA[k]; acc[1][k] += accC[k]; }
   }
-  if (partials_src) block_reduce_to_partials<D, 2>(acc, partials_src + (int64_t)blockIdx.x * 2 * D, red);
+  if (partials_src) {
+    block_reduce_to_partials<D, 2>(acc, partials_src + (int64_t)blockIdx.x * 2 * D, red);
+    const int extra = blockIdx.x + gridDim.x;              // rows [gridDim.x, partial_rows_total) belong to no block
+    if (extra < partial_rows_total)
+      for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) partials_src[(int64_t)extra * 2 * D + i] = 0.f;
+  }
 }
 
 // =============================================================================================
@@ -944,6 +949,8 @@ __global__ void segment_mean_backward_kernel(const float* __restrict__ g_out, co
 // C ABI
 // =============================================================================================
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 
 namespace alignn {
 std::atomic<uint64_t> g_launches{0};
@@ -955,6 +962,27 @@ int check_launch() {
   return ALIGNN_OK;
 }
 int record_cuda_error(int e) { g_last_cuda_error.store(e); return ALIGNN_ERR_CUDA; }
+int one_wave_grid(const void* kernel, int threads, size_t dyn_smem, int wanted_blocks) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> cache;
+  int resident;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(kernel);
+    if (it == cache.end()) {
+      int per_sm = 0, dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
+        per_sm = 1;
+      }
+      it = cache.emplace(kernel, per_sm * (sms > 0 ? sms : kNumSMs)).first;
+    }
+    resident = it->second;
+  }
+  return wanted_blocks < resident ? wanted_blocks : resident;
+}
 }  // namespace alignn
 
 namespace {
@@ -1104,7 +1132,12 @@ int alignn_b200_egc_backward(const alignn_b200_egc_bwd_args* a) {
 #undef LAUNCH_BWD_DST
   int rc = check_launch();
   if (rc != ALIGNN_OK) return rc;
-  DISPATCH_D(a->d, alignn::egc_backward_src_kernel<D><<<grid, alignn::kThreads, 0, st>>>(*a, a->partials_src));
+  DISPATCH_D(a->d, {
+    // `grid` partial rows are expected by the caller; the kernel runs as one wave and zeroes the rows no block owns
+    const int grid_src = alignn::one_wave_grid((const void*)alignn::egc_backward_src_kernel<D>, alignn::kThreads, 0, grid);
+    if (2 * grid_src < grid) return ALIGNN_ERR_CUDA;       // cannot happen on a device with >= 74 SMs
+    alignn::egc_backward_src_kernel<D><<<grid_src, alignn::kThreads, 0, st>>>(*a, a->partials_src, grid);
+  });
   return check_launch();
 }
 
@@ -1134,9 +1167,10 @@ int alignn_b200_bn_backward_apply(const float* R, const float* g_out, const floa
                                   float* gR, alignn_stream_t stream) {
   if (!supported_d(d)) return ALIGNN_ERR_UNSUPPORTED_D;
   if (n <= 0 || !R || !g_out || !scale || !shift || !mean || !rstd || !c1 || !c2 || !gR) return ALIGNN_ERR_BAD_ARG;
-  const int grid = grid_for_rows(n);
-  DISPATCH_D(d, alignn::bn_backward_apply_kernel<D><<<grid, alignn::kThreads, 0, (cudaStream_t)stream>>>(
-                    R, g_out, scale, shift, mean, rstd, c1, c2, n, gR));
+  DISPATCH_D(d, {
+    const int grid = alignn::one_wave_grid((const void*)alignn::bn_backward_apply_kernel<D>, alignn::kThreads, 0, grid_for_rows(n));
+    alignn::bn_backward_apply_kernel<D><<<grid, alignn::kThreads, 0, (cudaStream_t)stream>>>(R, g_out, scale, shift, mean, rstd, c1, c2, n, gR);
+  });
   return check_launch();
 }
 

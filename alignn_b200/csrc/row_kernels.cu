@@ -53,7 +53,7 @@ template <int D>
 __global__ void __launch_bounds__(kThreads)
 ln_silu_backward_kernel(const float* __restrict__ h, const float* __restrict__ g_out, const float2* __restrict__ rowstat,
                         const float* __restrict__ gamma, const float* __restrict__ beta, int64_t n, float* __restrict__ gh,
-                        float* __restrict__ partials) {
+                        float* __restrict__ partials, int partial_rows_total) {
   constexpr int V = RowCfg<D>::VPL;
   __shared__ float red[kWarpsPerBlock * D];
   const int lane = threadIdx.x & 31;
@@ -86,6 +86,9 @@ ln_silu_backward_kernel(const float* __restrict__ h, const float* __restrict__ g
     st_row<D, true>(gh + r * D, g, lane);
   }
   block_reduce_to_partials<D, 2>(acc, partials + (int64_t)blockIdx.x * 2 * D, red);
+  const int extra = blockIdx.x + gridDim.x;                // rows [gridDim.x, partial_rows_total) belong to no block
+  if (extra < partial_rows_total)
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) partials[(int64_t)extra * 2 * D + i] = 0.f;
 }
 
 // torch.optim.AdamW (amsgrad = False, maximize = False), element by element:
@@ -155,8 +158,11 @@ int alignn_b200_ln_silu_forward(const float* h, const float* gamma, const float*
   if (!supported_d(d)) return ALIGNN_ERR_UNSUPPORTED_D;
   if (n < 0 || (n > 0 && (!h || !gamma || !beta || !out || !rowstat))) return ALIGNN_ERR_BAD_ARG;
   if (n == 0) return ALIGNN_OK;
-  ROW_DISPATCH_D(d, alignn::ln_silu_forward_kernel<D><<<rows_grid(n), alignn::kThreads, 0, (cudaStream_t)stream>>>(
-                        h, gamma, beta, eps, n, out, reinterpret_cast<float2*>(rowstat)));
+  ROW_DISPATCH_D(d, {
+    const int grid = alignn::one_wave_grid((const void*)alignn::ln_silu_forward_kernel<D>, alignn::kThreads, 0, rows_grid(n));
+    alignn::ln_silu_forward_kernel<D><<<grid, alignn::kThreads, 0, (cudaStream_t)stream>>>(h, gamma, beta, eps, n, out,
+                                                                                         reinterpret_cast<float2*>(rowstat));
+  });
   return alignn::check_launch();
 }
 
@@ -166,8 +172,12 @@ int alignn_b200_ln_silu_backward(const float* h, const float* g_out, const float
   if (n < 0 || (n > 0 && (!h || !g_out || !rowstat || !gamma || !beta || !gh || !partials))) return ALIGNN_ERR_BAD_ARG;
   if (n == 0) return ALIGNN_OK;
   if (partial_rows != rows_grid(n)) return ALIGNN_ERR_WORKSPACE;
-  ROW_DISPATCH_D(d, alignn::ln_silu_backward_kernel<D><<<partial_rows, alignn::kThreads, 0, (cudaStream_t)stream>>>(
-                        h, g_out, reinterpret_cast<const float2*>(rowstat), gamma, beta, n, gh, partials));
+  ROW_DISPATCH_D(d, {
+    const int grid = alignn::one_wave_grid((const void*)alignn::ln_silu_backward_kernel<D>, alignn::kThreads, 0, partial_rows);
+    if (2 * grid < partial_rows) return ALIGNN_ERR_CUDA;
+    alignn::ln_silu_backward_kernel<D><<<grid, alignn::kThreads, 0, (cudaStream_t)stream>>>(
+        h, g_out, reinterpret_cast<const float2*>(rowstat), gamma, beta, n, gh, partials, partial_rows);
+  });
   return alignn::check_launch();
 }
 

@@ -422,7 +422,7 @@ def run_ours(args):
             reducer.reduce_flat()
             graph_opt.replay()
         compute_done[b].record(work)
-        loss_host[i % 2].copy_(loss_b, non_blocking=True)
+        loss_host[i % 2].copy_(loss_b.detach(), non_blocking=True)
         loss_ready[i % 2].record(work)
         prefetch(i + 1)                                       # overlaps with the step just launched
         if i > 0:
