@@ -104,7 +104,10 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, 
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 
-template <int BN, bool BNMODE>
+// MODE 0: bias / gathered addends / column statistics in the epilogue's row pass; 1: BatchNorm-backward sums in that pass;
+// 2: nothing row-wise (bias only, added in registers): accumulator -> swizzled box -> TMA store, no row pass;
+// 3: mode 0 with the first addend only and no statistics (data gradient + residual): half the addend registers.
+template <int BN, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapC, const Params p) {
   using F = Cfg<BN>;
@@ -235,8 +238,11 @@ gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     uint32_t chunk_ctr = 0;
     float* stat = reinterpret_cast<float*>(smem + F::OFF_STAT) + q * 2 * BN;
     const int half = ew >> 2;                                // which of the quarter's two warps: chunks half, half + 2, ...
-    const bool do_stats = p.stats != nullptr;
-    constexpr bool bnmode = BNMODE;
+    constexpr bool bnmode = MODE == 1;
+    constexpr bool plain = MODE == 2 && kTmaStore;
+    constexpr bool one = MODE == 3;                                       // add0 only, no add1, no statistics
+    constexpr bool late_wait = (plain || one) && kTmaStore;               // enough registers to hold a chunk across the wait
+    const bool do_stats = !plain && !one && p.stats != nullptr;
     if (do_stats)
       for (int ch = half; ch < BN / 32; ch += 2) { stat[ch * 32 + lane] = 0.f; stat[BN + ch * 32 + lane] = 0.f; }
     const int rsub = lane >> 3;                              // row within a group of 4
@@ -250,22 +256,25 @@ gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       // rows this lane finishes: it * 4 + rsub, it < 8.  i0 / i1 = addend row of each (-1: no addend / row past M)
       int i0[8], i1[8];
       uint32_t rvm = 0;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int gr = m0 + q * 32 + it * 4 + rsub;
-        const bool ok = gr < p.M;
-        rvm |= (ok ? 1u : 0u) << it;
-        i0[it] = (p.add0 && ok) ? (p.idx0 ? __ldg(p.idx0 + gr) : gr) : -1;
-        i1[it] = (p.add1 && ok) ? (p.idx1 ? __ldg(p.idx1 + gr) : gr) : -1;
-      }
       const float* base0 = p.add0 + n0 + c4 + half * 32;       // first chunk of this warp
       const float* base1 = p.add1 + n0 + c4 + half * 32;
       float4 a0[8], a1[8];
       const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (!plain) {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        a0[it] = (i0[it] >= 0 && half < NCH) ? __ldg(reinterpret_cast<const float4*>(base0 + (int64_t)i0[it] * p.ld0)) : z4;
-        a1[it] = (i1[it] >= 0 && half < NCH) ? __ldg(reinterpret_cast<const float4*>(base1 + (int64_t)i1[it] * p.ld1)) : z4;
+        for (int it = 0; it < 8; ++it) {
+          const int gr = m0 + q * 32 + it * 4 + rsub;
+          const bool ok = gr < p.M;
+          rvm |= (ok ? 1u : 0u) << it;
+          i0[it] = (p.add0 && ok) ? (p.idx0 ? __ldg(p.idx0 + gr) : gr) : -1;
+          if constexpr (!one) i1[it] = (p.add1 && ok) ? (p.idx1 ? __ldg(p.idx1 + gr) : gr) : -1;
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          a0[it] = (i0[it] >= 0 && half < NCH) ? __ldg(reinterpret_cast<const float4*>(base0 + (int64_t)i0[it] * p.ld0)) : z4;
+          if constexpr (!one)
+            a1[it] = (i1[it] >= 0 && half < NCH) ? __ldg(reinterpret_cast<const float4*>(base1 + (int64_t)i1[it] * p.ld1)) : z4;
+        }
       }
       tc::mbar_wait(&tfull[acc], (lt >> 1) & 1);
       tc::fence_after_sync();
@@ -274,18 +283,45 @@ gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       for (int ch = half; ch < NCH; ch += 2) {
         const int c0 = ch * 32;
         uint8_t* stg = stg0;
-        if (kTmaStore && chunk_ctr >= 1) {       // the TMA store that read this box must be done with it
+        // the TMA store that read this box must be done with it.  Modes 2 and 3 wait only after the TMEM load (the store's
+        // read of the box overlaps it); the others have no registers to keep the 32 values alive across the wait
+        if (!late_wait && kTmaStore && chunk_ctr >= 1) {
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
         }
-        ++chunk_ctr;
         {
           float v[32];
           tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
           if (ew == 0 && lane == 0) GEMM2_TRACE(5, tr5);
+          if (late_wait && chunk_ctr >= 1) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
+          ++chunk_ctr;
+          if constexpr (plain) {
+            // nothing row-wise to add: bias (the same 32 values for every lane) in registers, then straight to the store
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + 4 * j));
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              }
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(stg + st_row + ((j ^ st_sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if constexpr (plain) {
+          tc::fence_async_smem();
+          __syncwarp();
+          if (ew == 0 && lane == 0) GEMM2_TRACE(5, tr5);
+          if (lane == 0) {
+            tma_store_2d(&mapC, stg, n0 + c0, m0 + q * 32);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          __syncwarp();
+          continue;
         }
         __syncwarp();
         if (ew == 0 && lane == 0) GEMM2_TRACE(5, tr5);
@@ -304,7 +340,8 @@ gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
           const int r = it * 4 + rsub;
           float4* cell = reinterpret_cast<float4*>(stg + r * 128 + (((lane & 7) ^ (r & 7)) << 4));
           float4 o = *cell;
-          const float4 mrow = a1[it];                       // (BatchNorm mode: the pre-norm row, not an addend)
+          float4 mrow = z4;                                 // (BatchNorm mode: the pre-norm row, not an addend)
+          if constexpr (!one) mrow = a1[it];
           const float4 ad1 = bnmode ? z4 : mrow;
           o.x = (o.x + b4.x) + (a0[it].x + ad1.x);
           o.y = (o.y + b4.y) + (a0[it].y + ad1.y);
@@ -313,7 +350,8 @@ gemm_gather_bf16x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
           // this row's addends of the NEXT chunk go out now and land while the rest of this chunk is processed
           if (more) {
             if (i0[it] >= 0) a0[it] = __ldg(reinterpret_cast<const float4*>(base0 + (int64_t)i0[it] * p.ld0 + (c0 - half * 32) + 64));
-            if (i1[it] >= 0) a1[it] = __ldg(reinterpret_cast<const float4*>(base1 + (int64_t)i1[it] * p.ld1 + (c0 - half * 32) + 64));
+            if constexpr (!one)
+              if (i1[it] >= 0) a1[it] = __ldg(reinterpret_cast<const float4*>(base1 + (int64_t)i1[it] * p.ld1 + (c0 - half * 32) + 64));
           }
           if ((rvm >> it) & 1u) {
             if (bnmode) {
@@ -459,12 +497,12 @@ static long long* g_trace = nullptr;   // set by alignn_b200_debug_gemm_trace (d
 
 inline int pick_bn(int N) { return (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : (N % 32 == 0) ? 32 : 0; }
 
-template <int BN, bool BNMODE>
+template <int BN, int MODE>
 int launch2(const CUtensorMap& mapA, const CUtensorMap& mapC, const Params& p, cudaStream_t st) {
   using F = Cfg<BN>;
   static std::atomic<bool> configured{false};
   if (!configured.load(std::memory_order_acquire)) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_gather_bf16x3_kernel<BN, BNMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_gather_bf16x3_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
     if (e != cudaSuccess) return record_cuda_error((int)e);
     configured.store(true, std::memory_order_release);
   }
@@ -472,13 +510,16 @@ int launch2(const CUtensorMap& mapA, const CUtensorMap& mapC, const Params& p, c
   int grid = total < 148 ? total : 148;
   if (p.stats) grid = alignn_b200_gemm_gather_stat_rows(p.M, p.N) / p.stat_quarters;   // the caller sized `stats` for this many
                                                                       // CTAs (a CTA without tiles writes zeros)
-  gemm_gather_bf16x3_kernel<BN, BNMODE><<<grid, THREADS, F::SMEM, st>>>(mapA, mapC, p);
+  gemm_gather_bf16x3_kernel<BN, MODE><<<grid, THREADS, F::SMEM, st>>>(mapA, mapC, p);
   return check_launch();
 }
 
 template <int BN>
 int launch(const CUtensorMap& mapA, const CUtensorMap& mapC, const Params& p, cudaStream_t st) {
-  return p.bn_scale ? launch2<BN, true>(mapA, mapC, p, st) : launch2<BN, false>(mapA, mapC, p, st);
+  if (p.bn_scale) return launch2<BN, 1>(mapA, mapC, p, st);
+  if (kTmaStore && !p.add0 && !p.add1 && !p.stats) return launch2<BN, 2>(mapA, mapC, p, st);
+  if (p.add0 && !p.add1 && !p.stats) return launch2<BN, 3>(mapA, mapC, p, st);
+  return launch2<BN, 0>(mapA, mapC, p, st);
 }
 
 }  // namespace gemm2
