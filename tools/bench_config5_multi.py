@@ -15,7 +15,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from alignn_b200 import ops, synthetic  # noqa: E402
+from alignn_b200 import ops  # noqa: E402
+from alignn_b200.graph import Graph  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -46,8 +47,17 @@ def timed(fn, reps):
 
 out = {}
 for ne in (100_000, 1_000_000, 10_000_000):
-    g, bh, sigma = synthetic.make_segment_sweep(ne, d=256, seed=123 + rank)
-    gd, bh, sigma = g.to(dev), bh.to(dev), sigma.to(dev)
+    # the index as BASELINE config 5 defines it (synthetic.make_segment_sweep: fan-in 12, uniform random sources); the
+    # feature values are drawn on the device (10 GB of host random numbers per rank at 1e7 edges would dominate the run)
+    gen = torch.Generator().manual_seed(123 + rank)
+    nn_ = max(1, ne // 12)
+    dst = torch.repeat_interleave(torch.arange(nn_), 12)
+    src = torch.randint(0, nn_, (nn_ * 12,), generator=gen)
+    g = Graph(src, dst, nn_)
+    gd = g.to(dev)
+    dgen = torch.Generator(device=dev).manual_seed(7 + rank)
+    sigma = torch.rand(nn_ * 12, 256, device=dev, generator=dgen)
+    bh = torch.randn(nn_, 256, device=dev, generator=dgen)
 
     def run():
         return ops.gather_segment_sum(gd.index, bh, sigma)

@@ -14,12 +14,12 @@ for n in 2 4 8; do
   port=$((port + 1))
   timeout 300 $TR --nproc-per-node $n --master-port $port tools/bench_config5_multi.py 2> "$OUT/config5_n$n.err" | tail -1 > "$OUT/r${R}_config5_n$n.json"
 done
-for n in 2 4 8; do
+for n in ${BENCH_NS:-8}; do
   port=$((port + 1))
   timeout 400 $TR --nproc-per-node $n --master-port $port bench.py --gpus $n --steps 20 --warmup 3 2> "$OUT/bench_n$n.err" | tail -1 > "$OUT/r${R}_bench_n$n.json"
 done
 port=$((port + 1))
-ALIGNN_B200_NCCL_IN_GRAPH=1 timeout 400 $TR --nproc-per-node 8 --master-port $port bench.py --gpus 8 --steps 20 --warmup 3 2> "$OUT/bench_n8_ig.err" | tail -1 > "$OUT/r${R}_bench_n8_allreduce_in_graph.json"
+[ "${IN_GRAPH:-0}" = "1" ] && ALIGNN_B200_NCCL_IN_GRAPH=1 timeout 400 $TR --nproc-per-node 8 --master-port $port bench.py --gpus 8 --steps 20 --warmup 3 2> "$OUT/bench_n8_ig.err" | tail -1 > "$OUT/r${R}_bench_n8_allreduce_in_graph.json"
 python - "$OUT" "$R" <<'PY'
 import json, sys
 out, r = sys.argv[1], sys.argv[2]
