@@ -20,8 +20,15 @@ python tools/bench_gemm_gather.py | tail -1 > "$OUT/r${R}_gemm_gather_ab.json"
 ncu --set full --clock-control none --import-source on \
     -k regex:"egc_|wgrad_bf16x3|gemm_gather|affine_silu|bn_backward_reduce" -s 12 -c 12 \
     -o "$OUT/r${R}_final_bn" -f python tools/run_kernels.py conv_bn 2 > "$OUT/ncu_full.log" 2>&1
-python tools/ncu_summary.py "$OUT/r${R}_final_bn.ncu-rep" > "$OUT/r${R}_ncu_full_summary.md"
-python tools/ncu_traffic.py "$OUT/r${R}_final_bn.ncu-rep" > "$OUT/r${R}_ncu_traffic.json"
+# ... and the kernels that do not occur in a single conv: batched weight gradients, LayerNorm + SiLU rows, flat AdamW
+ncu --set full --clock-control none --import-source on \
+    -k regex:"wgrad_batch|ln_silu|adamw_flat" -s 3 -c 4 \
+    -o "$OUT/r${R}_final_extras" -f python tools/run_kernels.py extras 2 > "$OUT/ncu_full_extras.log" 2>&1
+python tools/ncu_summary.py "$OUT/r${R}_final_bn.ncu-rep" "$OUT/r${R}_final_extras.ncu-rep" > "$OUT/r${R}_ncu_full_summary.md"
+python tools/ncu_traffic.py "$OUT/r${R}_final_bn.ncu-rep" "$OUT/r${R}_final_extras.ncu-rep" > "$OUT/r${R}_ncu_traffic.json"
+python tools/trace_gemm.py plain > "$OUT/r${R}_gemm_trace.txt" 2>&1
+python tools/trace_gemm.py gate >> "$OUT/r${R}_gemm_trace.txt" 2>&1
+python tools/bench_egc_ring.py | tail -1 > "$OUT/r${R}_egc_ring_ab.json"
 # launch list of one training step (eager launches; graph replays launch the same kernels)
 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file "$OUT/r${R}_launches_all.csv" python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline \

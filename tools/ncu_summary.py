@@ -8,6 +8,11 @@ KEYS = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"),
         ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps %"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
+        ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "LSU pipe %"),
+        ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long-sb"),
+        ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short-sb"),
+        ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait"),
         ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"), ("launch__block_size", "block")]
 print("| report | kernel | " + " | ".join(k[1] for k in KEYS) + " |")
 print("|---|---|" + "---|" * len(KEYS))

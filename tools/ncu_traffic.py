@@ -12,25 +12,24 @@ NAMES = [("gemm_gather_bf16x3_kernel<256, false>|gather", "gemm_gather<256>+gath
          ("wgrad_bf16x3_kernel", "wgrad<256,256>"),
          ("bn_backward_reduce_kernel", "bn_backward_reduce"),
          ("affine_silu_residual_kernel", "affine_silu_residual")]
-rep = sys.argv[1]
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-hdr = rows[0]
-ik = hdr.index("Kernel Name")
-ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
-units = rows[1]
-
-
 def to_bytes(v, u):
     v = float(v.replace(",", ""))
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
 
 
+rep = sys.argv[1]                 # (the first report names the source of the per-conv kernels; more reports may follow)
 per = {}
-for r in rows[2:]:
-    name = r[ik]
-    b = to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw])
-    per.setdefault(name, []).append((b, r[it] + " " + units[it]))
+for one in sys.argv[1:]:
+    out = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr = rows[0]
+    ik = hdr.index("Kernel Name")
+    ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+    units = rows[1]
+    for r in rows[2:]:
+        name = r[ik]
+        b = to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw])
+        per.setdefault(name, []).append((b, r[it] + " " + units[it]))
 res = {}
 gemm = sorted(((max(v)[0], k, max(v)[1]) for k, v in per.items() if "gemm_gather" in k), reverse=True)
 for k, v in per.items():
@@ -40,7 +39,7 @@ for k, v in per.items():
 # aliases under the names bench.py's KernelTimer uses
 alias = {}
 for short, e in res.items():
-    if "egc_forward_kernel" in short:
+    if "egc_forward_kernel" in short or "egc_forward_ring_kernel" in short:
         alias["egc_forward<gate_is_m>"] = e
     if "wgrad_bf16x3_kernel<256, 256>" in short:
         alias["wgrad<256,256>"] = e
@@ -48,6 +47,12 @@ for short, e in res.items():
         alias["bn_backward_reduce"] = e
     if "affine_silu_residual_kernel<256>" in short:
         alias["affine_silu_residual"] = e
+    if "wgrad_batch_kernel<256, 256>" in short:
+        alias["wgrad_batch<256>"] = e
+    if "ln_silu_forward_kernel<256>" in short:
+        alias["ln_silu_forward"] = e
+    if "ln_silu_backward_kernel<256>" in short:
+        alias["ln_silu_backward"] = e
 d = [e for s, e in res.items() if "egc_backward_dst" in s]
 s_ = [e for s, e in res.items() if "egc_backward_src" in s]
 if d and s_:

@@ -38,5 +38,31 @@ if which in ("conv_bn", "conv_ln", "all"):
         for _ in range(reps):
             xo, yo = conv(lg, mi, zi)
             (xo.sum() + yo.sum()).backward()
+if which in ("extras", "all"):
+    # the batched weight gradients of one training step (4 x T rows, 12 x E rows, 8 x 4 x N rows), the LayerNorm + SiLU row
+    # kernels of an embedding layer at T rows, and the flat AdamW
+    from alignn_b200 import dp
+    N = g.num_nodes()
+    gm, gp, x = torch.randn(T, d, device=dev), torch.randn(E, 4 * d, device=dev), torch.randn(N, d, device=dev)
+    gpn = torch.randn(N, 4 * d, device=dev)
+    probs = []
+    for _ in range(4):
+        probs.append((gm, z, torch.empty(d, d, device=dev)))
+        probs += [(gp[:, j * d:(j + 1) * d], m, torch.empty(d, d, device=dev)) for j in range(4)]
+    for _ in range(8):
+        probs.append((m, m, torch.empty(d, d, device=dev)))
+        probs += [(gpn[:, j * d:(j + 1) * d], x, torch.empty(d, d, device=dev)) for j in range(4)]
+    layer = torch.nn.Sequential(torch.nn.Linear(64, d), torch.nn.LayerNorm(d), torch.nn.SiLU()).to(dev)
+    from alignn_b200.alignn import mlp_forward
+    h = torch.randn(T, 64, device=dev, requires_grad=True)
+    flat = torch.nn.Parameter(torch.randn(4_100_000, device=dev))
+    red = dp.FlatGradAllReducer([flat])
+    flat.grad = torch.randn_like(flat)
+    red.gather()
+    opt = dp.FlatAdamW(red)
+    for _ in range(reps):
+        ops.wgrad_batch(probs)
+        mlp_forward(layer, h).sum().backward()
+        opt.step()
 torch.cuda.synchronize()
 print("done", which)
