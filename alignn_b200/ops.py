@@ -6,6 +6,7 @@ tensors or if the library reports an error -- there is no fallback path.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 import weakref
 from typing import Optional, Tuple
@@ -15,6 +16,27 @@ import torch
 from . import _lib
 from ._lib import NORM_AFFINE, NORM_LAYER, NORM_STATS, ptr, require_cuda, stream_ptr  # noqa: F401
 from .graph import EdgeIndex
+
+
+def _on_tensor_device(fn):
+    """Launch on the device the operands live on, whatever the current device is (a model on cuda:1 in a process whose
+    current device is cuda:0 would otherwise enqueue on the wrong device and stream)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        dev = None
+        for a in args:
+            if isinstance(a, EdgeIndex):
+                a = a.src
+            elif isinstance(a, (list, tuple)) and a and isinstance(a[0], (list, tuple)) and a[0]:
+                a = a[0][0]
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                dev = a.device
+                break
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+    return wrapper
 
 
 class KernelTimer:
@@ -73,6 +95,7 @@ def partial_rows(num_nodes: int, d: int) -> int:
     return int(_lib.load().alignn_b200_egc_partial_rows(num_nodes, d))
 
 
+@_on_tensor_device
 def egc_forward(ix: EdgeIndex, x, y, G, P, n_w, n_b, e_w, e_b, *, norm_nodes: int, norm_edges: int,
                 residual: bool, save: bool, need_edge_out: bool, gate_eps: float = 1e-6, ln_eps: float = 1e-5,
                 gate_is_m: bool = False):
@@ -116,6 +139,7 @@ def egc_forward(ix: EdgeIndex, x, y, G, P, n_w, n_b, e_w, e_b, *, norm_nodes: in
     return dict(x_out=x_out, y_out=y_out, M=M, XP=XP, S=S, H=H, partials=partials)
 
 
+@_on_tensor_device
 def bn_finalize(partials, which: int, count: int, gamma, beta, eps: float, momentum: float,
                 running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor]):
     """Batch statistics -> (scale, shift, mean, rstd); updates running stats in place."""
@@ -129,6 +153,7 @@ def bn_finalize(partials, which: int, count: int, gamma, beta, eps: float, momen
     return out[0], out[1], out[2], out[3]
 
 
+@_on_tensor_device
 def affine_silu_residual(R, res, scale, shift):
     lib = _lib.load()
     n, d = R.shape
@@ -141,6 +166,7 @@ def affine_silu_residual(R, res, scale, shift):
     return out
 
 
+@_on_tensor_device
 def colsum(a: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
     """Deterministic fp64-accumulated column sum of a 2-D fp32 tensor (used on partial buffers)."""
     lib = _lib.load()
@@ -190,6 +216,7 @@ def bn_backward_finish(partials: torch.Tensor, n: int, rstd: torch.Tensor) -> Tu
     return c[:d], c[d:] * rstd
 
 
+@_on_tensor_device
 def bn_backward_reduce(R, g_out, scale, shift, mean, rstd) -> Tuple[torch.Tensor, torch.Tensor]:
     """c1 = mean(gu), c2 = mean(gu*xhat) per channel (BatchNorm train-mode backward, pass 1)."""
     lib = _lib.load()
@@ -205,6 +232,7 @@ def bn_backward_reduce(R, g_out, scale, shift, mean, rstd) -> Tuple[torch.Tensor
     return c[:d], c[d:]
 
 
+@_on_tensor_device
 def egc_backward(ix: EdgeIndex, P, M, XP, S, H, gx_out, gy_out, n, e, *, norm_nodes: int, norm_edges: int,
                  gate_eps: float = 1e-6, ln_eps: float = 1e-5):
     """n / e: dicts with keys w, b, mean, rstd, c1, c2 (entries may be None).
@@ -239,6 +267,7 @@ def egc_backward(ix: EdgeIndex, P, M, XP, S, H, gx_out, gy_out, n, e, *, norm_no
     return GM, GP, colsum(part).view(6, d), colsum(part_src).view(2, d)
 
 
+@_on_tensor_device
 def gather_segment_sum(ix: EdgeIndex, Bh, sigma):
     """Sh[v] = sum_{e->v} Bh[src e] * sigma[e];  S[v] = sum_{e->v} sigma[e]  (alignn.py:105-108)."""
     lib = _lib.load()
@@ -253,6 +282,7 @@ def gather_segment_sum(ix: EdgeIndex, Bh, sigma):
     return Sh, S
 
 
+@_on_tensor_device
 def pair_force_scatter(pair_forces: torch.Tensor, ix: EdgeIndex, add_reverse: bool = True) -> torch.Tensor:
     """forces[v] = sum over in-edges of pair_forces - (add_reverse ? sum over out-edges : 0): DGL's
     update_all(copy_e, sum) on g and on dgl.reverse(g) (alignn_atomwise.py:547-563) in one deterministic kernel."""
@@ -267,6 +297,7 @@ def pair_force_scatter(pair_forces: torch.Tensor, ix: EdgeIndex, add_reverse: bo
     return out
 
 
+@_on_tensor_device
 def virial_stress(r: torch.Tensor, pair_forces: torch.Tensor, edge_offsets64: torch.Tensor, node_offsets64: torch.Tensor,
                   V: torch.Tensor, multiplier: float = 1.0) -> torch.Tensor:
     """stress[b] = multiplier * -160.21766208 * (r_b^T F_b) / V[first atom of b], one block per crystal
@@ -305,6 +336,7 @@ class _SegmentMean(torch.autograd.Function):
         return gx, None
 
 
+@_on_tensor_device
 def segment_mean(x: torch.Tensor, graph_ptr: torch.Tensor) -> torch.Tensor:
     """Per-graph mean over node rows (dgl.nn.AvgPooling, alignn.py:325)."""
     return _SegmentMean.apply(x.contiguous(), graph_ptr)
@@ -470,6 +502,7 @@ def ptr_any(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+@_on_tensor_device
 def gemm_nt(A: torch.Tensor, w: WeightImage, bias: Optional[torch.Tensor] = None,
             residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = A[M,K] @ W^T (+ bias) (+ residual) on tcgen05.  A may be a column slice (row stride >= K)."""
@@ -491,6 +524,7 @@ def gemm_nt(A: torch.Tensor, w: WeightImage, bias: Optional[torch.Tensor] = None
     return out
 
 
+@_on_tensor_device
 def gemm_gather(A: torch.Tensor, w: WeightImage, bias: Optional[torch.Tensor] = None, *,
                 add0: Optional[torch.Tensor] = None, idx0: Optional[torch.Tensor] = None,
                 add1: Optional[torch.Tensor] = None, idx1: Optional[torch.Tensor] = None,
@@ -557,6 +591,7 @@ def wgrad_supported(DA: int, DB: int) -> bool:
     return int(_lib.load().alignn_b200_wgrad_workspace_bytes(32, DA, DB, 1)) > 0
 
 
+@_on_tensor_device
 def wgrad(A: torch.Tensor, B: torch.Tensor, groups: int = 1) -> torch.Tensor:
     """out[g*DA + o, i] = sum_r A[r, g*DA + o] * B[r, i]  (dL/dW of a Linear: A = output grads, B = inputs)."""
     lib = _lib.load()
@@ -579,6 +614,7 @@ def wgrad(A: torch.Tensor, B: torch.Tensor, groups: int = 1) -> torch.Tensor:
 WGRAD_BATCH_MAX = 64      # problems per launch (kMaxProblems in csrc/wgrad_tc.cu)
 
 
+@_on_tensor_device
 def wgrad_batch(problems) -> None:
     """ONE launch for many square weight gradients: `problems` is a list of (A [K, >= d] view, B [K, >= d] view, out [d, d]
     view); out[o, i] = sum_r A[r, o] * B[r, i].  Views may be column slices of wider matrices (row stride = stride(0))."""
@@ -641,6 +677,7 @@ class WgradQueue:
         wgrad_batch(items)
 
 
+@_on_tensor_device
 def colsum_rows(a: torch.Tensor) -> torch.Tensor:
     """Column sums of a tall contiguous [n, d] matrix, deterministic two-stage reduction."""
     lib = _lib.load()
@@ -719,6 +756,7 @@ def tc_linear_supported(in_features: int, out_features: int) -> bool:
     return out_features in _lib.SUPPORTED_D and wgrad_supported(out_features, k_pad)
 
 
+@_on_tensor_device
 def tc_linear(x: torch.Tensor, lin) -> torch.Tensor:
     """nn.Linear forward/backward on the tensor-core kernels; the input width is zero-padded to a multiple of 32."""
     tbl = linear_table(lin)
@@ -822,12 +860,14 @@ class _MLPLNFn(torch.autograd.Function):
         return gx, gw, gb, gwb[:d], gwb[d:], None, None
 
 
+@_on_tensor_device
 def mlp_ln(x, lin, ln):
     tbl = linear_table(lin)
     tbl.refresh()
     return _MLPLNFn.apply(x, lin.weight, lin.bias, ln.weight, ln.bias, ln.eps, tbl)
 
 
+@_on_tensor_device
 def mlp_bn_train(x, lin, bn):
     tbl = linear_table(lin)
     tbl.refresh()

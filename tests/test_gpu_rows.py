@@ -199,3 +199,26 @@ def test_forward_ring_kernel_is_bit_identical_to_register_kernel(d, mode):
             assert (a is None) == (b is None), k
             if a is not None:
                 assert torch.equal(a, b), (k, sort)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_kernels_follow_the_tensors_device_not_the_current_device():
+    """A model on cuda:1 in a process whose current device is cuda:0 (plain `model.to('cuda:1')`, no set_device) gives the
+    same numbers as on cuda:0: every wrapper launches on the device and stream of its operands."""
+    from alignn_b200 import synthetic
+    from alignn_b200.alignn import ALIGNN, ALIGNNConfig
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        torch.manual_seed(0)
+        model = ALIGNN(ALIGNNConfig(name="alignn", alignn_layers=1, gcn_layers=1, hidden_features=64, embedding_features=32)).to(dev).train()
+        g, lg, lat, tgt = (t.to(dev) for t in synthetic.make_batch(4, 8, 12, seed=2, vary_atoms=True))
+        red = dp.FlatGradAllReducer(model.parameters())
+        assert torch.cuda.current_device() == 0
+        for _ in range(2):
+            red.zero_grad()
+            with red.deferring():
+                (model((g, lg, lat)) - tgt).abs().mean().backward()
+            red.gather()
+        torch.cuda.synchronize(dev)
+        outs.append(red.flat.cpu())
+    assert torch.equal(outs[0], outs[1])
