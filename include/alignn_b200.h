@@ -409,7 +409,7 @@ int alignn_b200_segment_mean_backward(const float* g_out /*[B,d]*/, const int32_
  * ---------------------------------------------------------------------------------------- */
 void alignn_b200_debug_gemm_flags(int flags);               /* knock-out bits of the round-1 register-fed GEMM (gemm_nt) */
 void alignn_b200_debug_gemm_pair(int enabled);              /* route N = 256, K <= 256 gemm_gather calls to the two-CTA kernel */
-void alignn_b200_debug_egc_flags(int flags);                /* bit 0 / bit 1: register-staged instead of ring-staged egc forward / backward */
+void alignn_b200_debug_egc_flags(int flags);                /* bit 0: register-staged pass 2 instead of the ring; bit 1: channel-half egc_backward_dst (d = 256, BatchNorm) instead of the full-row kernel */
 void alignn_b200_debug_gemm_trace(long long* device_buffer); /* per-role SM-clock timeline of CTA 0 of gemm_gather ([6][512]) */
 
 #ifdef __cplusplus
