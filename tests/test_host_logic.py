@@ -298,3 +298,50 @@ def test_flat_adamw_equals_per_parameter_adamw():
     for pa, pb in zip(a.parameters(), b.parameters()):
         assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-7)
     assert torch.equal(b[3].weight, dead_before)
+
+
+def test_wgrad_batch_workspace_plan_on_the_host():
+    """The slab planner behind alignn_b200_wgrad_batch runs on the host (no GPU needed): the workspace is one D x D fp32
+    tile per slab, at least one slab per non-empty problem, never more than problems + 2 x 148 slabs, 0 for bad input."""
+    import ctypes as C
+    from alignn_b200 import _lib
+    lib = _lib.load()
+
+    def ws(Ks, d=256):
+        arr = (_lib.WgradProblem * len(Ks))()
+        for q, k in zip(arr, Ks):
+            q.K = k
+        return int(lib.alignn_b200_wgrad_batch_workspace_bytes(arr, len(Ks), d))
+    tile = 256 * 256 * 4
+    step = [276480] * 4 + [23040] * 24 + [1920] * 32               # one training step of the 4+4 stack at batch 64
+    n = ws(step) // tile
+    assert ws(step) % tile == 0 and len(step) <= n <= len(step) + 2 * 148
+    assert ws([0]) == tile and ws([0, 0, 5]) == tile                 # empty problems need no slab (one tile minimum)
+    assert ws([10 ** 7]) // tile >= 100                              # one huge problem is spread over the whole device
+    small = ws([1920] * 8)
+    assert 8 <= small // tile <= 8 + 2 * 148
+    assert ws([1, 2, 3], d=48) == 0 and ws([-1]) == 0               # unsupported width / negative K
+    assert ws([5] * 65) == 0                                         # more problems than one launch holds
+    assert ws([100] * 64, d=32) % (32 * 32 * 4) == 0
+
+
+def test_deferring_is_a_no_op_on_cpu_tensors():
+    """FlatGradAllReducer.deferring() only defers CUDA weight gradients; on CPU tensors backward + gather behave as usual."""
+    from alignn_b200 import dp
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.SiLU(), torch.nn.Linear(8, 8))
+    x = torch.randn(5, 8)
+    red = dp.FlatGradAllReducer(m.parameters())
+    flats = []
+    for deferred in (False, True, True):
+        red.zero_grad()
+        if deferred:
+            with red.deferring():
+                m(x).square().mean().backward()
+        else:
+            m(x).square().mean().backward()
+        red.gather()
+        flats.append(red.flat.clone())
+    assert torch.equal(flats[0], flats[1]) and torch.equal(flats[1], flats[2])
+    from alignn_b200 import ops
+    assert ops.WgradQueue.current is None
