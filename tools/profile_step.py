@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
-from alignn_b200 import synthetic  # noqa: E402
+from alignn_b200 import dp, synthetic  # noqa: E402
 from alignn_b200.alignn import ALIGNN, ALIGNNConfig  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -27,20 +27,28 @@ if args.norm == "layernorm":
 else:
     model = ALIGNN(ALIGNNConfig(name="alignn"))
 model.to(dev).train(not args.infer)
-opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
 g, lg, lat, tgt = [t.to(dev) for t in synthetic.make_batch(64, 30, 12, seed=123)]
+# the step bench.py times: flat gradient buffer, weight gradients deferred into one batched launch, one-launch AdamW
+reducer = dp.FlatGradAllReducer(model.parameters())
+opt = None
 
 
 def step():
     if args.infer:
         with torch.no_grad():
             return model((g, lg, lat))
-    opt.zero_grad(set_to_none=True)
+    reducer.zero_grad()
     loss = (model((g, lg, lat)) - tgt).abs().mean()
-    loss.backward()
-    opt.step()
+    with reducer.deferring():
+        loss.backward()
+    reducer.all_reduce()
+    if opt is not None:
+        opt.step()
 
 
+step()
+if not args.infer:
+    opt = dp.FlatAdamW(reducer, lr=1e-3)
 for _ in range(3):
     step()
 torch.cuda.synchronize()
