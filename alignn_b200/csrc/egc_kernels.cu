@@ -892,7 +892,7 @@ affine_silu_residual_kernel(const float* __restrict__ R, const float* __restrict
 }
 
 template <int D>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 bn_backward_reduce_kernel(const float* __restrict__ R, const float* __restrict__ g_out, const float* __restrict__ scale,
                           const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
                           int64_t n, float* __restrict__ partials) {
@@ -905,28 +905,27 @@ bn_backward_reduce_kernel(const float* __restrict__ R, const float* __restrict__
   ld_vec<D>(sc, scale, lane); ld_vec<D>(sh, shift, lane); ld_vec<D>(mu, mean, lane); ld_vec<D>(rs, rstd, lane);
 #pragma unroll
   for (int k = 0; k < V; ++k) { acc[0][k] = 0.f; acc[1][k] = 0.f; }
-  for (int64_t r = warp0; r < n; r += 2 * nwarps) {   // two rows in flight per warp
-    const int64_t r2 = r + nwarps;
-    const bool has2 = r2 < n;
-    float v[V], g[V], v2[V], g2[V];
-    ld_row<D, false>(v, R + r * D, lane);
-    ld_row<D, false>(g, g_out + r * D, lane);
-    if (has2) {
-      ld_row<D, false>(v2, R + r2 * D, lane);
-      ld_row<D, false>(g2, g_out + r2 * D, lane);
+  // four rows (eight row loads, 8 KB) in flight per warp: the kernel is latency-bound (stall long-scoreboard ~11 per
+  // issue with two rows), and the rows are consumed in the same order as before, so the sums keep their bits
+  for (int64_t r = warp0; r < n; r += 4 * nwarps) {
+    float v[4][V], g[4][V];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t rj = r + j * nwarps;
+      if (rj < n) {
+        ld_row<D, true>(v[j], R + rj * D, lane);
+        ld_row<D, true>(g[j], g_out + rj * D, lane);
+      }
     }
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      const float gu = g[k] * dsilu_(v[k] * sc[k] + sh[k]);
-      acc[0][k] += gu;
-      acc[1][k] += gu * (v[k] - mu[k]) * rs[k];
-    }
-    if (has2) {
+    for (int j = 0; j < 4; ++j) {
+      if (r + j * nwarps < n) {
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        const float gu = g2[k] * dsilu_(v2[k] * sc[k] + sh[k]);
-        acc[0][k] += gu;
-        acc[1][k] += gu * (v2[k] - mu[k]) * rs[k];
+        for (int k = 0; k < V; ++k) {
+          const float gu = g[j][k] * dsilu_(v[j][k] * sc[k] + sh[k]);
+          acc[0][k] += gu;
+          acc[1][k] += gu * (v[j][k] - mu[k]) * rs[k];
+        }
       }
     }
   }
