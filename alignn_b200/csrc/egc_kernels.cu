@@ -956,7 +956,7 @@ rowstats_partials_kernel(const float* __restrict__ a, int64_t n, float* __restri
 
 // BatchNorm1d(train) + SiLU backward, pass 2: gR = scale * (gu - c1 - xhat * c2), gu = g_out * silu'(R*scale+shift)
 template <int D>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 bn_backward_apply_kernel(const float* __restrict__ R, const float* __restrict__ g_out, const float* __restrict__ scale,
                          const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
                          const float* __restrict__ c1, const float* __restrict__ c2, int64_t n, float* __restrict__ gR) {
@@ -967,16 +967,30 @@ bn_backward_apply_kernel(const float* __restrict__ R, const float* __restrict__ 
   float sc[V], sh[V], mu[V], rs[V], k1[V], k2[V];
   ld_vec<D>(sc, scale, lane); ld_vec<D>(sh, shift, lane); ld_vec<D>(mu, mean, lane); ld_vec<D>(rs, rstd, lane);
   ld_vec<D>(k1, c1, lane); ld_vec<D>(k2, c2, lane);
-  for (int64_t r = warp0; r < n; r += nwarps) {
-    float v[V], g[V], o[V];
+  for (int64_t r = warp0; r < n; r += 2 * nwarps) {   // two rows (four row loads) in flight per warp
+    const int64_t r2 = r + nwarps;
+    const bool has2 = r2 < n;
+    float v[V], g[V], v2[V], g2[V];
     ld_row<D, true>(v, R + r * D, lane);
     ld_row<D, true>(g, g_out + r * D, lane);
+    if (has2) {
+      ld_row<D, true>(v2, R + r2 * D, lane);
+      ld_row<D, true>(g2, g_out + r2 * D, lane);
+    }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       const float gu = g[k] * dsilu_(v[k] * sc[k] + sh[k]);
-      o[k] = sc[k] * (gu - k1[k] - (v[k] - mu[k]) * rs[k] * k2[k]);
+      g[k] = sc[k] * (gu - k1[k] - (v[k] - mu[k]) * rs[k] * k2[k]);
     }
-    st_row<D, true>(gR + r * D, o, lane);
+    st_row<D, true>(gR + r * D, g, lane);
+    if (has2) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float gu = g2[k] * dsilu_(v2[k] * sc[k] + sh[k]);
+        g2[k] = sc[k] * (gu - k1[k] - (v2[k] - mu[k]) * rs[k] * k2[k]);
+      }
+      st_row<D, true>(gR + r2 * D, g2, lane);
+    }
   }
 }
 

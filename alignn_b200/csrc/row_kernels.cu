@@ -50,7 +50,7 @@ ln_silu_forward_kernel(const float* __restrict__ h, const float* __restrict__ ga
 // gh[r] = rstd * (gx - mean_c(gx) - xhat * mean_c(gx * xhat)),  gx = g_out * silu'(u) * gamma,  u = xhat * gamma + beta;
 // partials[block] = {sum_r g_out silu'(u) xhat  (-> d gamma),  sum_r g_out silu'(u)  (-> d beta)}
 template <int D>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 ln_silu_backward_kernel(const float* __restrict__ h, const float* __restrict__ g_out, const float2* __restrict__ rowstat,
                         const float* __restrict__ gamma, const float* __restrict__ beta, int64_t n, float* __restrict__ gh,
                         float* __restrict__ partials, int partial_rows_total) {
@@ -63,10 +63,7 @@ ln_silu_backward_kernel(const float* __restrict__ h, const float* __restrict__ g
   ld_vec<D>(w, gamma, lane); ld_vec<D>(b, beta, lane);
 #pragma unroll
   for (int k = 0; k < V; ++k) { acc[0][k] = 0.f; acc[1][k] = 0.f; }
-  for (int64_t r = warp0; r < n; r += nwarps) {
-    float v[V], g[V];
-    ld_row<D, true>(v, h + r * D, lane);
-    ld_row<D, true>(g, g_out + r * D, lane);
+  auto one_row = [&](int64_t r, float (&v)[V], float (&g)[V]) {
     const float2 st = __ldg(rowstat + r);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -84,6 +81,19 @@ ln_silu_backward_kernel(const float* __restrict__ h, const float* __restrict__ g
 #pragma unroll
     for (int k = 0; k < V; ++k) g[k] = st.y * (g[k] - s1 - v[k] * s2);
     st_row<D, true>(gh + r * D, g, lane);
+  };
+  for (int64_t r = warp0; r < n; r += 2 * nwarps) {        // two rows (four row loads) in flight per warp
+    const int64_t r2 = r + nwarps;
+    const bool has2 = r2 < n;
+    float v[V], g[V], v2[V], g2[V];
+    ld_row<D, true>(v, h + r * D, lane);
+    ld_row<D, true>(g, g_out + r * D, lane);
+    if (has2) {
+      ld_row<D, true>(v2, h + r2 * D, lane);
+      ld_row<D, true>(g2, g_out + r2 * D, lane);
+    }
+    one_row(r, v, g);
+    if (has2) one_row(r2, v2, g2);
   }
   block_reduce_to_partials<D, 2>(acc, partials + (int64_t)blockIdx.x * 2 * D, red);
   const int extra = blockIdx.x + gridDim.x;                // rows [gridDim.x, partial_rows_total) belong to no block
