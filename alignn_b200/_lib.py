@@ -75,6 +75,10 @@ class WgradProblem(C.Structure):
     _fields_ = [("A", _fp), ("lda", C.c_int64), ("B", _fp), ("ldb", C.c_int64), ("K", C.c_int64), ("out", _fp), ("ld_out", C.c_int64)]
 
 
+class ColsumProblem(C.Structure):
+    _fields_ = [("a", _fp), ("rows", C.c_int64), ("stride", C.c_int64), ("cols", C.c_int), ("alpha", C.c_float), ("out", _fp)]
+
+
 class ImageEntry(C.Structure):
     _fields_ = [("W", _fp), ("ldw", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32), ("transpose", C.c_int32),
                 ("n_off", C.c_int32), ("k_off", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("image", _fp)]
@@ -105,6 +109,7 @@ _SIGNATURES = {
                                          C.c_int, _fp, _fp, _fp]),
     "alignn_b200_colsum_partials": (C.c_int, [_fp, C.c_int64, C.c_int, _fp, C.c_int, _fp]),
     "alignn_b200_colsum": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_int64, C.c_float, _fp, _fp]),
+    "alignn_b200_colsum_batch": (C.c_int, [C.POINTER(ColsumProblem), C.c_int, _fp]),
     "alignn_b200_gather_segment_sum": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int64, C.c_int, _fp, _fp, _fp]),
     "alignn_b200_gemm_weight_image_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "alignn_b200_gemm_prepare_weights": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int64, C.c_int, _fp, _fp]),

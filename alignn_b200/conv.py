@@ -224,6 +224,7 @@ class _EdgeGatedConvFn(torch.autograd.Function):
                 cfg.legacy_w = (Wcat, W_eg)
             ctx.save_for_backward(x, y, P, out["M"], out["XP"], out["S"], out["H"], nw, nb, ew, eb)
             ctx.weights = (W_sg, W_dg, W_eg, W_su, W_du)          # identities only: ops.WgradQueue maps them to destinations
+            ctx.biases = (b_sg, b_dg, b_eg, b_su, b_du)
         ctx.y_dead = y_out is None
         if y_out is None:       # dead edge output (or an edgeless graph): hand autograd an empty placeholder
             y_out = x.new_empty((0, d))
@@ -262,7 +263,17 @@ class _EdgeGatedConvFn(torch.autograd.Function):
                         ops.bn_backward_reduce(M, gy_out, e["w"], e["b"], e["mean"], e["rstd"])
                 fk.join()
                 n["c1"], n["c2"] = cn
-        GM, GP, vd, vs = ops.egc_backward(cfg.index, P, M, XP, S, H, gx_out, gy_out, n, e,
+        # Parameter gradients are off the critical path of backward.  With a queue installed (FlatGradAllReducer.deferring())
+        # the five weight-gradient GEMMs and the nine bias / norm-parameter reductions of this conv are only registered
+        # here and computed by two batched launches at the end of backward, straight into the flat gradient buffer.
+        params = not ops.input_grads_only.active                # a forces-only backward discards every parameter gradient
+        queue = ops.WgradQueue.current
+        W_sg, W_dg, W_eg, W_su, W_du = ctx.weights
+        b_sg, b_dg, b_eg, b_su, b_du = ctx.biases
+        vec_needed = [b_sg, b_dg, b_eg, b_su, b_du, nw, nb] + ([ew, eb] if gy_out is not None else [])
+        deferred = params and queue is not None and ops.wgrad_supported(d, d) and queue.wants(W_sg, W_du, W_dg, W_su, W_eg) \
+            and queue.wants_vecs(*vec_needed)
+        GM, GP, vd, vs = ops.egc_backward(cfg.index, P, M, XP, S, H, gx_out, gy_out, n, e, reduce=params and not deferred,
                                           norm_nodes=cfg.norm_nodes, norm_edges=cfg.norm_edges,
                                           gate_eps=GATE_EPS, ln_eps=cfg.ln_eps)
         # GEMM halves of the backward on the tensor cores: data gradients (gemm_fused_tc.cu, transposed weight images,
@@ -273,15 +284,21 @@ class _EdgeGatedConvFn(torch.autograd.Function):
         fk = _Fork(x.device)
         if need[1]:
             gx = fk.on(0, lambda: ops.gemm_gather(GP, img_catT, None, add0=gx_out if cfg.residual else None))
-        params = not ops.input_grads_only.active                # a forces-only backward discards every parameter gradient
-        queue = ops.WgradQueue.current
-        W_sg, W_dg, W_eg, W_su, W_du = ctx.weights
-        deferred = params and queue is not None and ops.wgrad_supported(d, d) and queue.wants(W_sg, W_du, W_dg, W_su, W_eg)
         if deferred:
-            # weight gradients are off the critical path: queued, computed by ONE batched launch at the end of backward
             for j, W in enumerate((W_sg, W_du, W_dg, W_su)):           # column blocks of GP: e_src | Bh | e_dst | src_update
                 queue.add(GP[:, j * d:(j + 1) * d], x, W)
             queue.add(GM, y, W_eg)
+            # partial rows of the destination pass: {g_ew, g_eb, g_nw, g_nb, gb_su, gb_dg}; of the source pass: {gb_sg, gb_du}
+            if gy_out is not None:
+                queue.add_vec(vd, 0, d, ew)
+                queue.add_vec(vd, 1, d, eb)
+            queue.add_vec(vd, 2, d, nw)
+            queue.add_vec(vd, 3, d, nb)
+            queue.add_vec(vd, 4, d, b_su)
+            queue.add_vec(vd, 5, d, b_dg)
+            queue.add_vec(vd, 5, d, b_eg)                            # sum_e gm_e == sum_v sum_{e->v} gm_e
+            queue.add_vec(vs, 0, d, b_sg)
+            queue.add_vec(vs, 1, d, b_du)
         elif params:
             gWcat = fk.on(1, lambda: ops.wgrad(GP, x, groups=4))      # [4d, d] rows: src_gate | dst_update | dst_gate | src_update
             gW_eg = fk.on(2, lambda: ops.wgrad(GM, y, groups=1))
@@ -299,9 +316,8 @@ class _EdgeGatedConvFn(torch.autograd.Function):
         if not params:
             return (None, gx, gy) + (None,) * 14
         if deferred:
-            gW_sg = gW_du = gW_dg = gW_su = gW_eg = None
-        else:
-            gW_sg, gW_du, gW_dg, gW_su = gWcat[0:d], gWcat[d:2 * d], gWcat[2 * d:3 * d], gWcat[3 * d:4 * d]
+            return (None, gx, gy) + (None,) * 14
+        gW_sg, gW_du, gW_dg, gW_su = gWcat[0:d], gWcat[d:2 * d], gWcat[2 * d:3 * d], gWcat[3 * d:4 * d]
         gb_sg, gb_du = vs[0], vs[1]
         gb_su, gb_dg = vd[4], vd[5]
         gb_eg = gb_dg                           # sum_e gm_e == sum_v sum_{e->v} gm_e

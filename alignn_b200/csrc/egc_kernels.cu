@@ -1034,6 +1034,29 @@ colsum_kernel(const float* __restrict__ a, int64_t rows, int cols, int64_t strid
   out[c] = alpha * (float)s;
 }
 
+// Many column sums in one launch: problem p sums `cols` columns of its own partial buffer into its own output vector
+// (the bias / norm-parameter gradients of every conv of a backward pass: 100+ vectors of d floats, each the fixed-order
+// fp64 sum of <= 592 partial rows).  blockIdx.y = problem, blockIdx.x = 32-column chunk; same arithmetic as colsum_kernel.
+struct ColsumProblem { const float* a; float* out; int64_t rows, stride; int cols; float alpha; };
+constexpr int kMaxColsumProblems = 192;
+struct ColsumBatch { ColsumProblem p[kMaxColsumProblems]; };
+__global__ void __launch_bounds__(1024)
+colsum_batch_kernel(const __grid_constant__ ColsumBatch bt) {
+  __shared__ double ss[32][33];
+  const ColsumProblem& q = bt.p[blockIdx.y];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double s = 0.0;
+  if (c < q.cols)
+    for (int64_t r = rl; r < q.rows; r += 32) s += (double)q.a[r * q.stride + c];
+  ss[rl][cl] = s;
+  __syncthreads();
+  if (rl != 0 || c >= q.cols) return;
+#pragma unroll
+  for (int k = 1; k < 32; ++k) s += ss[k][cl];
+  q.out[c] = q.alpha * (float)s;
+}
+
 // =============================================================================================
 // Gather / segment-sum primitive (DGL u_mul_e -> sum and copy_e -> sum in one pass)
 // =============================================================================================
@@ -1375,6 +1398,26 @@ int alignn_b200_colsum(const float* a, int64_t rows, int cols, int64_t stride, f
   if (!a || !out || rows < 0 || cols <= 0 || stride < cols) return ALIGNN_ERR_BAD_ARG;
   alignn::colsum_kernel<<<(cols + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(a, rows, cols, stride, alpha, out);
   return check_launch();
+}
+
+int alignn_b200_colsum_batch(const alignn_b200_colsum_problem* problems, int n, alignn_stream_t stream) {
+  if (!problems || n < 0) return ALIGNN_ERR_BAD_ARG;
+  static thread_local alignn::ColsumBatch bt;
+  for (int i0 = 0; i0 < n; i0 += alignn::kMaxColsumProblems) {
+    const int m = n - i0 < alignn::kMaxColsumProblems ? n - i0 : alignn::kMaxColsumProblems;
+    int max_cols = 0;
+    for (int i = 0; i < m; ++i) {
+      const alignn_b200_colsum_problem& q = problems[i0 + i];
+      if (!q.a || !q.out || q.rows < 0 || q.cols <= 0 || q.stride < q.cols) return ALIGNN_ERR_BAD_ARG;
+      bt.p[i].a = q.a; bt.p[i].out = q.out; bt.p[i].rows = q.rows; bt.p[i].stride = q.stride; bt.p[i].cols = q.cols;
+      bt.p[i].alpha = q.alpha;
+      if (q.cols > max_cols) max_cols = q.cols;
+    }
+    alignn::colsum_batch_kernel<<<dim3((max_cols + 31) / 32, m), 1024, 0, (cudaStream_t)stream>>>(bt);
+    int rc = check_launch();
+    if (rc != ALIGNN_OK) return rc;
+  }
+  return ALIGNN_OK;
 }
 
 int alignn_b200_gather_segment_sum(const float* Bh, const float* sigma, const int32_t* src, const int32_t* in_ptr,

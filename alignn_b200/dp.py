@@ -93,6 +93,7 @@ class FlatGradAllReducer:
             return
         self.queue.dest = {p.data_ptr(): v for p, v in zip(self.active, self.views)
                            if p.dim() == 2 and p.shape[0] == p.shape[1] and v.data_ptr() % 16 == 0}
+        self.queue.vec_dest = {p.data_ptr(): v for p, v in zip(self.active, self.views) if p.dim() == 1}
 
     def deferring(self):
         """Context manager for `loss.backward()`: the conv layers queue their weight-gradient GEMMs instead of launching

@@ -233,11 +233,12 @@ def bn_backward_reduce(R, g_out, scale, shift, mean, rstd) -> Tuple[torch.Tensor
 
 
 @_on_tensor_device
-def egc_backward(ix: EdgeIndex, P, M, XP, S, H, gx_out, gy_out, n, e, *, norm_nodes: int, norm_edges: int,
+def egc_backward(ix: EdgeIndex, P, M, XP, S, H, gx_out, gy_out, n, e, *, reduce: bool = True, norm_nodes: int, norm_edges: int,
                  gate_eps: float = 1e-6, ln_eps: float = 1e-5):
     """n / e: dicts with keys w, b, mean, rstd, c1, c2 (entries may be None).
 
-    Returns GM [Ne,d], GP [Nn,4d], vec_dst [6,d], vec_src [2,d] (column sums of the partials)."""
+    Returns GM [Ne,d], GP [Nn,4d], vec_dst [6,d], vec_src [2,d] (column sums of the partials); with reduce=False the
+    per-block partial rows [rows, 6d] and [rows, 2d] themselves."""
     lib = _lib.load()
     Nn, d = XP.shape
     Ne = M.shape[0]
@@ -264,6 +265,8 @@ def egc_backward(ix: EdgeIndex, P, M, XP, S, H, gx_out, gy_out, n, e, *, norm_no
     nb = 4 * d * (Ne * (2 + (gy_out is not None)) + 9 * Nn) + 12 * Ne + 4 * d * 2 * Ne
     with _span("egc_backward(dst+src)", nb):
         _lib.check(lib.alignn_b200_egc_backward(C.byref(a)), "alignn_b200_egc_backward")
+    if not reduce:              # the caller sums the per-block partial rows itself (WgradQueue: one batched launch per backward)
+        return GM, GP, part, part_src
     return GM, GP, colsum(part).view(6, d), colsum(part_src).view(2, d)
 
 
@@ -655,26 +658,54 @@ class WgradQueue:
     current: Optional["WgradQueue"] = None
 
     def __init__(self):
-        self.dest = {}            # weight.data_ptr() -> destination view
+        self.dest = {}            # weight.data_ptr() -> destination view [d, d]
+        self.vec_dest = {}        # bias / norm parameter data_ptr() -> destination view [d]
         self.items = []           # (A, B, out)
+        self.vec_items = []       # (partial rows [rows, n*d], column offset, d, out)
         self._seen = set()
 
     def wants(self, *weights) -> bool:
         keys = [w.data_ptr() for w in weights]
         return all(k in self.dest and k not in self._seen for k in keys) and len(set(keys)) == len(keys)
 
+    def wants_vecs(self, *params) -> bool:
+        keys = [p.data_ptr() for p in params]
+        return all(k in self.vec_dest and k not in self._seen for k in keys) and len(set(keys)) == len(keys)
+
     def add(self, A: torch.Tensor, B: torch.Tensor, weight: torch.Tensor) -> None:
         k = weight.data_ptr()
         self._seen.add(k)
         self.items.append((A, B, self.dest[k]))
+
+    def add_vec(self, partials: torch.Tensor, block: int, d: int, param: torch.Tensor) -> None:
+        """param.grad = column sums of partials[:, block*d:(block+1)*d] (per-block partial rows of egc_backward)."""
+        k = param.data_ptr()
+        self._seen.add(k)
+        self.vec_items.append((partials, block * d, d, self.vec_dest[k]))
 
     def deferred_ptrs(self):
         return self._seen
 
     def flush(self) -> None:
         items, self.items = self.items, []
+        vecs, self.vec_items = self.vec_items, []
         self._seen = set()
         wgrad_batch(items)
+        colsum_batch(vecs)
+
+
+@_on_tensor_device
+def colsum_batch(problems) -> None:
+    """ONE launch for many column sums: `problems` = list of (partials [rows, >= off + d], off, d, out [d])."""
+    if not problems:
+        return
+    lib = _lib.load()
+    arr = (_lib.ColsumProblem * len(problems))()
+    for q, (part, off, d, out) in zip(arr, problems):
+        if not (part.is_cuda and out.is_cuda and part.dtype == out.dtype == torch.float32) or part.stride(1) != 1 or out.numel() != d:
+            raise RuntimeError("colsum_batch: fp32 CUDA partial rows with unit column stride and a [d] output")
+        q.a, q.rows, q.stride, q.cols, q.alpha, q.out = part.data_ptr() + 4 * off, part.shape[0], part.stride(0), d, 1.0, ptr(out)
+    _lib.check(lib.alignn_b200_colsum_batch(arr, len(problems), stream_ptr()), "alignn_b200_colsum_batch")
 
 
 @_on_tensor_device

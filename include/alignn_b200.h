@@ -214,6 +214,17 @@ int alignn_b200_colsum_partials(const float* a, int64_t n, int d, float* partial
 int alignn_b200_colsum(const float* a, int64_t rows, int cols, int64_t stride, float alpha, float* out,
                        alignn_stream_t stream);
 
+/* Many column sums in one launch (same arithmetic as alignn_b200_colsum per problem): the bias and norm-parameter
+ * gradients of all convs of a backward pass -- autograd's reductions of `alignn.py:98-127` over the per-block partial rows
+ * alignn_b200_egc_backward leaves -- are off the critical path and are summed together at the end of backward.
+ * `problems` is a HOST array (copied into the kernel parameters; capturable in a CUDA graph). */
+typedef struct {
+  const float* a; int64_t rows; int64_t stride;   /* [rows, >= cols] partial rows, row stride in floats */
+  int cols; float alpha;
+  float* out;                                     /* [cols] */
+} alignn_b200_colsum_problem;
+int alignn_b200_colsum_batch(const alignn_b200_colsum_problem* problems, int n, alignn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Gather / segment-sum primitive alone (BASELINE.json config 5; DGL update_all(u_mul_e,sum) +
  * update_all(copy_e,sum), alignn.py:105-108):  Sh[v] = sum_{e->v} Bh[src e]*sigma[e],
