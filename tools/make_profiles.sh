@@ -33,13 +33,7 @@ python tools/bench_egc_ring.py | tail -1 > "$OUT/r${R}_egc_ring_ab.json"
 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file "$OUT/r${R}_launches_all.csv" python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline \
     > "$OUT/ncu_launches.log" 2>&1
-python - "$OUT/r${R}_launches_all.csv" "$OUT/r${R}_launches_bench_step.csv" <<'PY'
-import sys
-lines = open(sys.argv[1]).read().splitlines()
-hdr = [i for i, l in enumerate(lines) if l.startswith('"ID"')][0]
-rows = lines[hdr + 1:]
-open(sys.argv[2], "w").write("\n".join([lines[hdr]] + rows[-340:]) + "\n")     # the last (timed) step
-PY
+python tools/last_step_launches.py "$OUT/r${R}_launches_all.csv" "$OUT/r${R}_launches_bench_step.csv"
 python tools/launch_table.py "$OUT/r${R}_launches_bench_step.csv" > "$OUT/r${R}_launch_table.txt"
 # sanitizers on a subset of the parity tests
 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_gemm.py -q -x \
