@@ -144,10 +144,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": gps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "model": "ALIGNN 4+4 d=256 (" + args.norm + ", train mode)",
-                   "global_batch": graphs, "per_gpu_batch": graphs, "parallelism": "dp1", "optimizer": "AdamW", "loss": "L1",
-                   "device": "host cores (reference arm)",
-                   "sample": f"{graphs} graphs per step" + ("" if graphs == args.batch else " (bounded CPU sample of the 64-graph batch)")},
+        # the workload keys are the same in both arms (the reference arm times a bounded sample of it: cpu_baseline.sample)
+        "config": {"workload": WORKLOAD, "norm": args.norm, "global_batch": args.batch * args.gpus, "per_gpu_batch": args.batch,
+                   "parallelism": f"dp{args.gpus}", "optimizer": "AdamW", "loss": "L1",
+                   "l2": "not applicable (host cores)"},
+        "run": {"device": "host cores (reference arm)",
+                "sample": f"{graphs} graphs per step" + ("" if graphs == args.batch else " (bounded CPU sample of the 64-graph batch)")},
         "cpu_baseline": {"value": gps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps x {graphs} graphs, torch-CPU restatement of the reference DGL path "
                                    f"(DGL is not installable offline); thread count calibrated on the same step over "
@@ -506,15 +508,15 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "model": "ALIGNN 4+4 d=256 (" + args.norm + ", train mode)",
-                   "global_batch": graphs_per_step, "per_gpu_batch": args.batch, "N": N, "E": E, "T": T,
+        "config": {"workload": WORKLOAD, "norm": args.norm, "global_batch": graphs_per_step, "per_gpu_batch": args.batch,
                    "parallelism": f"dp{world}", "optimizer": "AdamW", "loss": "L1",
-                   "device": "B200", "optimizer_impl": "one launch over one flat parameter (alignn_b200.dp.FlatAdamW -> alignn_b200_adamw_flat)",
-                   "cuda_graph": use_graph, "allreduce_in_graph": bool(nccl_in_graph), "eager_ms_per_step": ms_eager / args.steps,
-                   "timing": f"median of {len(reps_res)} repetitions of exactly {args.steps} steps (each: events on the launching "
-                             f"stream, barrier + synchronize on both sides, max over ranks)",
-                   "repetition_ms": [round(m, 3) for m in reps_res],
                    "l2": f"no explicit flush: per-step working set ~{sbytes / 1e9:.1f} GB >> 126 MB L2; 4 batches rotate"},
+        "run": {"device": "B200", "N": N, "E": E, "T": T,
+                "optimizer_impl": "one launch over one flat parameter (alignn_b200.dp.FlatAdamW -> alignn_b200_adamw_flat)",
+                "cuda_graph": use_graph, "allreduce_in_graph": bool(nccl_in_graph), "eager_ms_per_step": ms_eager / args.steps,
+                "timing": f"median of {len(reps_res)} repetitions of exactly {args.steps} steps (each: events on the launching "
+                          f"stream, barrier + synchronize on both sides, max over ranks)",
+                "repetition_ms": [round(m, 3) for m in reps_res]},
         "roofline": roofline,
         "step_hbm": {"algorithmic_bytes_per_step": sbytes, "achieved": sbytes / (ms_step * 1e-3) / 1e9, "peak": peak,
                      "unit": "GB/s", "frac": sbytes / (ms_step * 1e-3) / 1e9 / peak,
