@@ -574,6 +574,8 @@ inline bool shape_ok(int DA, int DB) {
 }  // namespace wgrad
 }  // namespace alignn
 
+constexpr int kBatchNeedsFallback = -1000;     // internal: cooperative launch refused, run the problems one by one
+
 template <int D>
 static int launch_batch(const alignn::wgrad::Batch& bt, float* ws, cudaStream_t st) {
   using namespace alignn::wgrad;
@@ -587,6 +589,10 @@ static int launch_batch(const alignn::wgrad::Batch& bt, float* ws, cudaStream_t 
   void* args[] = {(void*)&bt, (void*)&ws};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)wgrad_batch_kernel<D, D>, dim3(kNumSMsWgrad), dim3(THREADS), args,
                                               (size_t)F::SMEM, st);
+  if (e == cudaErrorCooperativeLaunchTooLarge) {     // the device cannot co-schedule 148 CTAs right now (MPS slice, ...)
+    (void)cudaGetLastError();
+    return kBatchNeedsFallback;
+  }
   if (e != cudaSuccess) return alignn::record_cuda_error((int)e);
   return alignn::check_launch();
 }
@@ -636,7 +642,7 @@ int alignn_b200_wgrad_batch(const alignn_b200_wgrad_problem* problems, int n, in
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     coop_ok = (coop && sms >= kNumSMsWgrad) ? 1 : 0;
   }
-  if (!coop_ok) {       // no co-scheduled grid on this device: one launch per problem through the two-launch path
+  auto one_by_one = [&]() -> int {   // no co-scheduled grid on this device: one launch per problem through the single-problem path
     for (int p = 0; p < n; ++p) {
       const alignn_b200_wgrad_problem& q = problems[p];
       if (workspace_bytes < alignn_b200_wgrad_workspace_bytes(q.K, D, D, 1)) return ALIGNN_ERR_WORKSPACE;
@@ -644,16 +650,22 @@ int alignn_b200_wgrad_batch(const alignn_b200_wgrad_problem* problems, int n, in
       if (rc != ALIGNN_OK) return rc;
     }
     return ALIGNN_OK;
-  }
+  };
+  if (!coop_ok) return one_by_one();
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = reinterpret_cast<float*>(workspace);
+  int rc = ALIGNN_ERR_UNSUPPORTED_D;
   switch (D) {
-    case 256: return launch_batch<256>(bt, ws, st);
-    case 128: return launch_batch<128>(bt, ws, st);
-    case 64: return launch_batch<64>(bt, ws, st);
-    case 32: return launch_batch<32>(bt, ws, st);
+    case 256: rc = launch_batch<256>(bt, ws, st); break;
+    case 128: rc = launch_batch<128>(bt, ws, st); break;
+    case 64: rc = launch_batch<64>(bt, ws, st); break;
+    case 32: rc = launch_batch<32>(bt, ws, st); break;
   }
-  return ALIGNN_ERR_UNSUPPORTED_D;
+  if (rc == kBatchNeedsFallback) {
+    coop_ok = 0;
+    return one_by_one();
+  }
+  return rc;
 }
 
 int alignn_b200_wgrad(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int DA, int DB, int groups,
