@@ -111,8 +111,12 @@ class FlatGradAllReducer:
                 self.prev = ops.WgradQueue.current
                 ops.WgradQueue.current = red.queue
 
-            def __exit__(self, *exc):
+            def __exit__(self, exc_type, *exc):
                 ops.WgradQueue.current = self.prev
+                if exc_type is not None:          # a failed backward: drop what it queued (its operands are garbage)
+                    red.queue.items.clear()
+                    red.queue.vec_items.clear()
+                    red.queue.deferred_ptrs().clear()
         return _Ctx()
 
     def zero_grad(self) -> None:

@@ -345,3 +345,18 @@ def test_deferring_is_a_no_op_on_cpu_tensors():
     assert torch.equal(flats[0], flats[1]) and torch.equal(flats[1], flats[2])
     from alignn_b200 import ops
     assert ops.WgradQueue.current is None
+
+
+def test_deferring_drops_the_queue_when_backward_raises():
+    from alignn_b200 import dp, ops
+    m = torch.nn.Linear(4, 4)
+    red = dp.FlatGradAllReducer(m.parameters())
+    m(torch.randn(2, 4)).sum().backward()
+    red.gather()
+    with pytest.raises(RuntimeError):
+        with red.deferring():
+            red.queue.items.append(("stale", "stale", "stale"))
+            red.queue.deferred_ptrs().add(123)
+            raise RuntimeError("backward failed")
+    assert red.queue.items == [] and red.queue.vec_items == [] and not red.queue.deferred_ptrs()
+    assert ops.WgradQueue.current is None
