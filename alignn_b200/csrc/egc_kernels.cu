@@ -6,6 +6,7 @@
 // Reference math: alignn/models/alignn.py:98-127.  P is the [Nn,4d] node
 // projection in the layout documented in include/alignn_b200.h: [e_src | Bh | e_dst | src_update].
 #include "common.cuh"
+#include "api_common.h"
 #include "alignn_b200.h"
 
 namespace alignn {
@@ -1246,12 +1247,12 @@ int alignn_b200_egc_forward(const alignn_b200_egc_fwd_args* a) {
     if (a->gate_is_m && g_forward_ring.load()) {
       // rows staged through a shared-memory ring (cp.async); same results as egc_forward_kernel<D, true>
       const size_t ring_bytes = (size_t)(4 + alignn::kWarpsPerBlock * alignn::kRing * 3) * D * sizeof(float);
-      static bool configured = false;
-      if (!configured) {
+      static alignn::DeviceOnce configured; int cfg_dev;
+      if (configured.needed(&cfg_dev)) {
         cudaError_t e = cudaFuncSetAttribute(alignn::egc_forward_ring_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)ring_bytes);
         if (e != cudaSuccess) return alignn::record_cuda_error((int)e);
-        configured = true;
+        configured.done(cfg_dev);
       }
       alignn::egc_forward_ring_kernel<D><<<grid, alignn::kThreads, ring_bytes, st>>>(*a);
     } else if (a->gate_is_m) alignn::egc_forward_kernel<D, true><<<grid, alignn::kThreads, smem_bytes, st>>>(*a);
@@ -1307,24 +1308,24 @@ int alignn_b200_egc_backward(const alignn_b200_egc_bwd_args* a) {
 #define LAUNCH_BWD_DST(NORM)                                                                                   \
   DISPATCH_D(a->d, {                                                                                           \
     const size_t smem_bytes = (size_t)(alignn::kWarpsPerBlock * 8 + 12) * D * sizeof(float);                   \
-    static bool configured = false;                                                                            \
-    if (!configured) {                                                                                         \
+    static alignn::DeviceOnce configured; int cfg_dev;                                                                            \
+    if (configured.needed(&cfg_dev)) {                                                                                         \
       cudaError_t e = cudaFuncSetAttribute(alignn::egc_backward_dst_kernel<D, NORM>,                           \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);      \
       if (e != cudaSuccess) return alignn::record_cuda_error((int)e);                                          \
-      configured = true;                                                                                       \
+      configured.done(cfg_dev);                                                                                       \
     }                                                                                                          \
     alignn::egc_backward_dst_kernel<D, NORM><<<grid, alignn::kThreads, smem_bytes, st>>>(*a);                  \
   })
 #define LAUNCH_BWD_DST_HALF(NORM)                                                                              \
   {                                                                                                            \
     const size_t smem_bytes = (size_t)(alignn::kWarpsPerBlock * 6 + 12) * 256 * sizeof(float);                 \
-    static bool configured = false;                                                                            \
-    if (!configured) {                                                                                         \
+    static alignn::DeviceOnce configured; int cfg_dev;                                                                            \
+    if (configured.needed(&cfg_dev)) {                                                                                         \
       cudaError_t e = cudaFuncSetAttribute(alignn::egc_backward_dst_half_kernel<NORM>,                         \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);      \
       if (e != cudaSuccess) return alignn::record_cuda_error((int)e);                                          \
-      configured = true;                                                                                       \
+      configured.done(cfg_dev);                                                                                       \
     }                                                                                                          \
     alignn::egc_backward_dst_half_kernel<NORM><<<grid, alignn::kThreads, smem_bytes, st>>>(*a);                \
   }

@@ -500,11 +500,11 @@ inline int pick_bn(int N) { return (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 :
 template <int BN, int MODE>
 int launch2(const CUtensorMap& mapA, const CUtensorMap& mapC, const Params& p, cudaStream_t st) {
   using F = Cfg<BN>;
-  static std::atomic<bool> configured{false};
-  if (!configured.load(std::memory_order_acquire)) {
+  static alignn::DeviceOnce configured; int cfg_dev;
+  if (configured.needed(&cfg_dev)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_gather_bf16x3_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
     if (e != cudaSuccess) return record_cuda_error((int)e);
-    configured.store(true, std::memory_order_release);
+    configured.done(cfg_dev);
   }
   const int total = ((p.M + BM - 1) / BM) * (p.N / BN);
   int grid = total < 148 ? total : 148;

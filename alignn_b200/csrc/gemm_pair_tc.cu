@@ -427,11 +427,11 @@ gemm_gather_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
 static std::atomic<int> g_pair_enabled{0};   // opt-in: correct on B200 but slower than the one-CTA kernel at these shapes
 
 int launch_pair(const CUtensorMap& mapA, const CUtensorMap& mapC, const Params& p, cudaStream_t st) {
-  static std::atomic<bool> configured{false};
-  if (!configured.load(std::memory_order_acquire)) {
+  static alignn::DeviceOnce configured; int cfg_dev;
+  if (configured.needed(&cfg_dev)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_gather_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return record_cuda_error((int)e);
-    configured.store(true, std::memory_order_release);
+    configured.done(cfg_dev);
   }
   const int total = (p.M + 2 * BM - 1) / (2 * BM);
   const int pairs = total < 74 ? total : 74;

@@ -351,11 +351,11 @@ template <int BN>
 int launch_gemm(const float* A, int64_t lda, const void* img, int M, int N, int K, const float* bias, const float* R,
                 int64_t ldr, float* C, int64_t ldc, cudaStream_t st) {
   using F = Cfg<BN>;
-  static bool configured = false;   // idempotent attribute; a benign race sets it twice
-  if (!configured) {
+  static alignn::DeviceOnce configured; int cfg_dev;   // idempotent attribute; a benign race sets it twice
+  if (configured.needed(&cfg_dev)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_nt_bf16x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
     if (e != cudaSuccess) return record_cuda_error((int)e);
-    configured = true;
+    configured.done(cfg_dev);
   }
   const int total = ((M + BM - 1) / BM) * (N / BN);
   const int grid = total < 148 ? total : 148;          // persistent: one CTA per SM

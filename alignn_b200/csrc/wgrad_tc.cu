@@ -528,11 +528,11 @@ template <int DA, int DB>
 int launch(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int groups, float* out, int64_t ld_out,
            float* ws, cudaStream_t st) {
   using F = Cfg<DA, DB>;
-  static bool configured = false;
-  if (!configured) {
+  static alignn::DeviceOnce configured; int cfg_dev;
+  if (configured.needed(&cfg_dev)) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_bf16x3_kernel<DA, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
     if (e != cudaSuccess) return record_cuda_error((int)e);
-    configured = true;
+    configured.done(cfg_dev);
   }
   const int ctas = ctas_for(K, groups);
   int64_t rows = (K + ctas - 1) / ctas;
@@ -580,11 +580,11 @@ template <int D>
 static int launch_batch(const alignn::wgrad::Batch& bt, float* ws, cudaStream_t st) {
   using namespace alignn::wgrad;
   using F = Cfg<D, D>;
-  static bool configured = false;
-  if (!configured) {
+  static alignn::DeviceOnce configured; int cfg_dev;
+  if (configured.needed(&cfg_dev)) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_batch_kernel<D, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
     if (e != cudaSuccess) return alignn::record_cuda_error((int)e);
-    configured = true;
+    configured.done(cfg_dev);
   }
   void* args[] = {(void*)&bt, (void*)&ws};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)wgrad_batch_kernel<D, D>, dim3(kNumSMsWgrad), dim3(THREADS), args,
