@@ -360,3 +360,16 @@ def test_deferring_drops_the_queue_when_backward_raises():
             raise RuntimeError("backward failed")
     assert red.queue.items == [] and red.queue.vec_items == [] and not red.queue.deferred_ptrs()
     assert ops.WgradQueue.current is None
+
+
+def test_public_header_is_plain_c():
+    """include/alignn_b200.h is the drop-in boundary: it has to compile as C99 (cgo / ctypes / JNI style bindings), not only
+    as C++."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "alignn_b200.h")
+    r = subprocess.run([gcc, "-x", "c", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
